@@ -1,0 +1,271 @@
+"""Declarative description of the ACR network (HRNet-W32 trunk + SegmNet + heads).
+
+The reference builds this network out of nested ``nn.Module`` classes
+(/root/reference/acr/model.py:23-329 heads, :374-463 SegmNet, :470-539 blocks,
+:571-686 HighResolutionModule, :691-881 HigherResolutionNet).  Here the same
+topology is emitted as a flat op list (a tiny IR) that the launch-plan builder
+turns into kernel launches and that the parameter registry turns into a
+state-dict with the *reference's key names* (checkpoint compatibility,
+/root/reference/acr/utils.py:1106-1168).
+
+IR
+--
+``Tensor``  : per-image activation (C logical channels, H, W); stored NHWC.
+``Op``      : kind in {"stem","conv","fuse","bilinear2x","coordcat","pool",
+              "parthead"}; convs carry the state-dict keys of their weights.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, used by every BN in acr/model.py
+
+
+@dataclass
+class Tensor:
+    name: str
+    C: int
+    H: int
+    W: int
+    dtype: str = "act"  # "act" = bf16/fp16 activation, "f32" = fp32 map
+    # channel view into a wider buffer (used for the 32+2 coord concat)
+    base: Optional["Tensor"] = None
+    c_off: int = 0
+
+
+@dataclass
+class Op:
+    kind: str
+    out: Tensor
+    ins: List[Tensor] = field(default_factory=list)
+    attrs: dict = field(default_factory=dict)
+
+
+class NetSpec:
+    """Op list + parameter registry (key -> (shape, kind))."""
+
+    def __init__(self):
+        self.ops: List[Op] = []
+        self.params: "OrderedDict[str, Tuple[Tuple[int, ...], str]]" = OrderedDict()
+        self.tensors: Dict[str, Tensor] = {}
+        self._n = 0
+
+    # ------------------------------------------------------------------ utils
+    def _t(self, C, H, W, hint, dtype="act") -> Tensor:
+        self._n += 1
+        t = Tensor(f"t{self._n}_{hint}", C, H, W, dtype)
+        self.tensors[t.name] = t
+        return t
+
+    def _reg(self, key, shape, kind):
+        assert key not in self.params, key
+        self.params[key] = (tuple(shape), kind)
+
+    def _reg_bn(self, key, c):
+        self._reg(key + ".weight", (c,), "bn_w")
+        self._reg(key + ".bias", (c,), "bn_b")
+        self._reg(key + ".running_mean", (c,), "bn_mean")
+        self._reg(key + ".running_var", (c,), "bn_var")
+        self._reg(key + ".num_batches_tracked", (), "bn_nbt")
+
+    # -------------------------------------------------------------------- ops
+    def conv(self, x: Tensor, wkey: str, bnkey: Optional[str], cout: int, k: int,
+             s: int = 1, relu: bool = False, bias: bool = False,
+             residual: Optional[Tensor] = None, out_dtype: str = "act",
+             out: Optional[Tensor] = None, hint: str = "") -> Tensor:
+        self._reg(wkey + ".weight", (cout, x.C, k, k), "conv_w")
+        if bias:
+            self._reg(wkey + ".bias", (cout,), "conv_b")
+        if bnkey:
+            self._reg_bn(bnkey, cout)
+        Ho, Wo = x.H // s, x.W // s
+        y = out if out is not None else self._t(cout, Ho, Wo, hint or wkey.split(".")[-1], out_dtype)
+        self.ops.append(Op("conv", y, [x] + ([residual] if residual is not None else []),
+                           dict(w=wkey, bn=bnkey, bias=bias, k=k, s=s, relu=relu,
+                                residual=residual is not None)))
+        return y
+
+    def fuse(self, terms: List[Tuple[Tensor, int]], relu=True, out: Optional[Tensor] = None) -> Tensor:
+        t0 = terms[0][0]
+        H, W = t0.H << terms[0][1], t0.W << terms[0][1]
+        y = out if out is not None else self._t(t0.C, H, W, "fuse")
+        self.ops.append(Op("fuse", y, [t for t, _ in terms],
+                           dict(shifts=[sh for _, sh in terms], relu=relu)))
+        return y
+
+
+# ---------------------------------------------------------------------------
+# HRNet-W32 trunk   (reference: HigherResolutionNet.make_baseline / forward,
+#                    acr/model.py:785-865)
+# ---------------------------------------------------------------------------
+WIDTHS = (32, 64, 128, 256)
+
+
+def _basic_block(g: NetSpec, x: Tensor, p: str, c: int) -> Tensor:
+    # acr/model.py:470-499  conv3x3-bn-relu, conv3x3-bn, += residual, relu
+    y = g.conv(x, p + ".conv1", p + ".bn1", c, 3, relu=True)
+    return g.conv(y, p + ".conv2", p + ".bn2", c, 3, relu=True, residual=x)
+
+
+def _bottleneck(g: NetSpec, x: Tensor, p: str, planes: int, down: bool) -> Tensor:
+    # acr/model.py:501-539  1x1 -> 3x3 -> 1x1(x4) (+ 1x1 downsample on the first block)
+    res = x
+    if down:
+        res = g.conv(x, p + ".downsample.0", p + ".downsample.1", planes * 4, 1)
+    y = g.conv(x, p + ".conv1", p + ".bn1", planes, 1, relu=True)
+    y = g.conv(y, p + ".conv2", p + ".bn2", planes, 3, relu=True)
+    return g.conv(y, p + ".conv3", p + ".bn3", planes * 4, 1, relu=True, residual=res)
+
+
+def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bool,
+               out0: Optional[Tensor] = None) -> List[Tensor]:
+    # acr/model.py:571-686; 4 BasicBlocks per branch, then the fuse layers
+    nb = len(xs)
+    xs = list(xs)
+    for b in range(nb):
+        for blk in range(4):
+            xs[b] = _basic_block(g, xs[b], f"{prefix}.branches.{b}.{blk}", WIDTHS[b])
+    outs = []
+    for i in range(nb if multi_scale_output else 1):
+        terms = []
+        for j in range(nb):
+            if j == i:
+                terms.append((xs[j], 0))
+            elif j > i:  # 1x1 conv + BN at low resolution, nearest-upsampled by 2**(j-i)
+                p = f"{prefix}.fuse_layers.{i}.{j}"
+                z = g.conv(xs[j], p + ".0", p + ".1", WIDTHS[i], 1)
+                terms.append((z, j - i))
+            else:        # chain of (i-j) stride-2 3x3 convs; ReLU on all but the last
+                t = xs[j]
+                for k in range(i - j):
+                    p = f"{prefix}.fuse_layers.{i}.{j}.{k}"
+                    last = k == i - j - 1
+                    t = g.conv(t, p + ".0", p + ".1", WIDTHS[i] if last else WIDTHS[j], 3, s=2,
+                               relu=not last)
+                terms.append((t, 0))
+        # reference sums in order j = 0..nb-1 (acr/model.py:677-684)
+        outs.append(g.fuse(terms, relu=True, out=out0 if i == 0 else None))
+    return outs
+
+
+def build_acr_spec(input_size: int = 512) -> NetSpec:
+    """Full ACR network for one image of ``input_size`` x ``input_size``."""
+    g = NetSpec()
+    S = input_size
+    img = Tensor("image", 3, S, S, "u8")
+    g.tensors[img.name] = img
+
+    # ---- stem (acr/model.py:831-839): x/255*2-1, conv3x3 s2 + BN + ReLU, twice
+    g._reg("backbone.conv1.weight", (64, 3, 3, 3), "conv_w")
+    g._reg_bn("backbone.bn1", 64)
+    x = g._t(64, S // 2, S // 2, "stem1")
+    g.ops.append(Op("stem", x, [img], dict(w="backbone.conv1", bn="backbone.bn1")))
+    x = g.conv(x, "backbone.conv2", "backbone.bn2", 64, 3, s=2, relu=True)
+
+    # ---- layer1: 4 Bottlenecks 64 -> 256 (acr/model.py:794)
+    for i in range(4):
+        x = _bottleneck(g, x, f"backbone.layer1.{i}", 64, down=(i == 0))
+
+    # ---- transition1 + stage2 (acr/model.py:796-805, 841-847)
+    xs = [g.conv(x, "backbone.transition1.0.0", "backbone.transition1.0.1", 32, 3, relu=True),
+          g.conv(x, "backbone.transition1.1.0.0", "backbone.transition1.1.0.1", 64, 3, s=2, relu=True)]
+    xs = _hr_module(g, "backbone.stage2.0", xs, True)
+
+    # ---- transition2 + stage3 (4 modules, 3 branches)
+    xs.append(g.conv(xs[-1], "backbone.transition2.2.0.0", "backbone.transition2.2.0.1", 128, 3, s=2, relu=True))
+    for m in range(4):
+        xs = _hr_module(g, f"backbone.stage3.{m}", xs, True)
+
+    # ---- transition3 + stage4 (3 modules, 4 branches; last keeps only branch 0)
+    xs.append(g.conv(xs[-1], "backbone.transition3.3.0.0", "backbone.transition3.3.0.1", 256, 3, s=2, relu=True))
+    # the backbone output lands in channels [0:32) of the 34-channel coord-concat buffer
+    F = S // 4
+    xcat = g._t(34, F, F, "xcat")
+    feat = Tensor("feat32", 32, F, F, "act", base=xcat, c_off=0)
+    g.tensors[feat.name] = feat
+    for m in range(3):
+        last = m == 2
+        xs = _hr_module(g, f"backbone.stage4.{m}", xs, not last, out0=feat if last else None)
+    x = xs[0]
+    assert x is feat
+    # coord channels 32,33 are constants written once (acr/model.py:52, 340-369)
+    g.ops.append(Op("coordcat", xcat, [feat], {}))
+
+    # ---- SegmNet (acr/model.py:374-463): bilinear x2, DoubleConv 32->16->64, conv 64->33+BN+ReLU, conv 33->33
+    up = g._t(32, 2 * F, 2 * F, "bilin")
+    g.ops.append(Op("bilinear2x", up, [feat], {}))
+    pu = "backbone.hand_segm.segm_head.upsampler.up1.conv.double_conv"
+    y = g.conv(up, pu + ".0", pu + ".1", 16, 3, relu=True, bias=True)
+    y = g.conv(y, pu + ".3", pu + ".4", 64, 3, relu=True, bias=True)
+    ps = "backbone.hand_segm.segm_head.segm_net.double_conv"
+    y = g.conv(y, ps + ".0", ps + ".1", 33, 3, relu=True, bias=True)
+    segm = g.conv(y, ps + ".3", None, 33, 3, bias=True, hint="segm")
+    g.tensors["segms"] = segm
+
+    # ---- global heads (acr/model.py:68-101, 288-313): 8 stacks on the 34-ch map
+    heads = {}
+    for side in ("l", "r"):
+        for idx, (nm, co) in {1: ("params", 106), 2: ("center", 1), 3: ("cam", 3), 4: ("prior", 106)}.items():
+            p = f"{side}_final_layers.{idx}"
+            h = g.conv(xcat, p + ".0.0", p + ".0.1", 64, 3, s=2, relu=True, bias=True)
+            for blk in range(2):
+                h = _basic_block(g, h, f"{p}.1.{blk}.0", 64)
+            heads[(side, nm)] = g.conv(h, p + ".2", None, co, 1, bias=True, out_dtype="f32",
+                                       hint=f"{side}_{nm}")
+    for k, t in heads.items():
+        g.tensors[f"{k[0]}_{k[1]}_raw"] = t
+
+    # ---- part branch (acr/model.py:116-166)
+    contact = g.conv(xcat, "contact_layers.1.0", "contact_layers.1.1", 256, 3, relu=True, bias=True,
+                     hint="contact")
+    g._reg("cam_shape_layers.1.0.weight", (64, 256, 1, 1), "conv_w")
+    g._reg("cam_shape_layers.1.0.bias", (64,), "conv_b")
+    for i in (2, 3):
+        g._reg(f"contact_layers.{i}.weight", (1, 6, 256, 16, 1, 1), "lc_w")
+    for i in (2, 3):
+        g._reg(f"cam_shape_layers.{i}.weight", (10, 1024), "lin_w")
+        g._reg(f"cam_shape_layers.{i}.bias", (10,), "lin_b")
+    for i in (4, 5):
+        g._reg(f"contact_layers.{i}.weight", (109, 218, 1, 1), "conv_w")
+        g._reg(f"contact_layers.{i}.bias", (109,), "conv_b")
+    # attention pooling + per-joint heads + final 218->109 1x1 conv (folded, see plan builder)
+    pooled = g._t(256, 32, 1, "pooled", "f32")
+    g.ops.append(Op("pool", pooled, [contact, segm], {}))
+    g.tensors["pooled"] = pooled
+    for side in ("l", "r"):
+        t = g._t(109, F // 2, F // 2, f"{side}_params_maps", "f32")
+        g.ops.append(Op("parthead", t, [pooled, heads[(side, "cam")], heads[(side, "params")]],
+                        dict(side=side)))
+        g.tensors[f"{side}_params_maps"] = t
+        g.tensors[f"{side}_center_map"] = heads[(side, "center")]
+        g.tensors[f"{side}_prior_maps"] = heads[(side, "prior")]
+
+    # ---- dead-but-present parameters (acr/model.py:181, 262-286): kept so that
+    #      state_dict() has the reference's 2067 keys; never executed.
+    g._reg("segmentation_layers.1.0.weight", (256, 34, 3, 3), "conv_w")
+    g._reg("segmentation_layers.1.0.bias", (256,), "conv_b")
+    g._reg_bn("segmentation_layers.1.1", 256)
+    g._reg("segmentation_layers.2.0.weight", (33, 256, 1, 1), "conv_w")
+    g._reg("segmentation_layers.2.0.bias", (33,), "conv_b")
+    return g
+
+
+def conv_flops_per_image(spec: NetSpec) -> float:
+    """2*MAC count of every executed Conv2d/Linear + the two pooling matmuls
+    (102.12 GFLOP/img for HRNet-W32 at 512x512)."""
+    fl = 0.0
+    for op in spec.ops:
+        if op.kind == "conv":
+            x, y = op.ins[0], op.out
+            fl += 2.0 * y.H * y.W * y.C * x.C * op.attrs["k"] ** 2
+        elif op.kind == "stem":
+            fl += 2.0 * op.out.H * op.out.W * 64 * 27
+    F = spec.tensors["feat32"].H
+    fl += 2.0 * F * F * 64 * 256               # cam_shape_layers[1] 1x1 conv 256->64
+    fl += 2 * 2.0 * F * F * 109 * 218 / 4      # contact_layers[4,5] at (F/2)^2
+    fl += 2 * 2.0 * 1024 * 10                  # shape Linear
+    fl += 2 * 2.0 * 16 * 6 * 256               # LocallyConnected2d
+    fl += 2.0 * 32 * F * F * (256 + 64)        # Hadamard matmuls
+    return fl

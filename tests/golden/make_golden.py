@@ -1,0 +1,214 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference) on seeded synthetic inputs.  Runs only in the build container (the
+reference does not exist on the GPU box); the fixtures it writes are committed and are
+what pins the oracle (oracle/*.py) and, through it, the CUDA path.
+
+    python tests/golden/make_golden.py          # writes *.npz next to this file
+
+Harness steps follow SURVEY.md section 8c: reference root on sys.path + chdir, argv set
+before import, stub modules for absent imports that the hot path never executes,
+``ready_arguments`` replaced by a synthetic MANO asset, ``.cuda()`` neutralised on CPU.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+PKG = os.path.join(ROOT, "arbitrary-hands-3d-reconstruction_b200")
+REF = "/root/reference"
+
+
+def import_reference():
+    sys.argv = ["make_golden"]
+    sys.path.insert(0, PKG)        # for acr_b200.* only
+    sys.path.insert(0, REF)        # reference's acr / mano win the name lookup
+    os.chdir(REF)
+    for name in ("h5py", "imgaug", "imgaug.augmenters", "chumpy", "chumpy.ch"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+    sys.modules["imgaug.augmenters"].compute_paddings_to_reach_aspect_ratio = lambda *a, **k: None
+    sys.modules["chumpy"].Ch = object
+    sys.modules["chumpy"].ch = sys.modules["chumpy.ch"]
+    np.float = float
+    np.int = int
+    import torch
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    import acr.config  # noqa: F401  (parses argv + demo.yml at import)
+    import mano.manolayer as ml
+    from acr_b200.synth import make_synthetic_mano
+
+    class _R:  # mimic chumpy's ``.r``
+        def __init__(self, a):
+            self.r = a
+
+    def fake_ready_arguments(path, posekey4vposed="pose"):
+        import scipy.sparse as sp
+        side = "left" if "LEFT" in path else "right"
+        a = make_synthetic_mano(side)
+        d = {k: _R(v) for k, v in a.items() if k in ("betas", "shapedirs", "posedirs", "v_template", "weights")}
+        d["hands_components"] = a["hands_components"]
+        d["hands_mean"] = a["hands_mean"]
+        d["J_regressor"] = sp.csc_matrix(a["J_regressor"])
+        d["f"] = a["f"]
+        d["kintree_table"] = a["kintree_table"]
+        return d
+
+    ml.ready_arguments = fake_ready_arguments
+    return torch
+
+
+def main():
+    torch = import_reference()
+    torch.manual_seed(0)
+    from acr_b200.synth import synth_state_dict
+    import acr.model as ref_model
+    import acr.utils as ref_utils
+    from acr.mano_wrapper import MANOWrapper
+    from mano.manolayer import batch_rodrigues
+
+    # ------------------------------------------------------------------ rotations
+    rng = np.random.default_rng(7)
+    r6 = rng.standard_normal((64, 6)).astype(np.float32)
+    r6[0] = [1, 0, 0, 1, 0, 0]                    # identity
+    r6[1] = [1, 0, 0, -1, 0, 0]                   # 180 deg about x  (trace = -1)
+    r6[2] = [-1, 0, 0, 1, 0, 0]                   # 180 deg about y
+    r6[3] = [-1, 0, 0, -1, 0, 0]                  # 180 deg about z
+    r6[4] = [1e-9, 0, 0, 0, 0, 1e-9]              # degenerate (below normalize eps)
+    r6[5] = [1, 1, 2, 2, 3, 3]                    # parallel columns
+    r6[6] = [0, 0, 0, 0, 0, 0]
+    aa = ref_utils.rot6D_to_angular(torch.from_numpy(r6.reshape(4, 96))).numpy()
+    aa_in = (rng.standard_normal((40, 3)) * 1.2).astype(np.float32)
+    aa_in[0] = 0
+    aa_in[1] = [np.pi, 0, 0]
+    aa_in[2] = [1e-7, -1e-7, 1e-7]
+    aa_in[3] = [0, 3.1415925, 0]
+    rod = batch_rodrigues(torch.from_numpy(aa_in)).numpy()
+    np.savez_compressed(os.path.join(HERE, "rot_golden.npz"), rot6d=r6.reshape(4, 96), aa=aa,
+                        aa_in=aa_in, rodrigues=rod)
+
+    # ----------------------------------------------------------------------- MANO
+    mw = MANOWrapper().eval()
+    n = 10
+    poses = (rng.standard_normal((n, 48)) * 0.5).astype(np.float32)
+    betas = rng.standard_normal((n, 10)).astype(np.float32)
+    poses[0] = 0
+    betas[0] = 0
+    poses[1, :3] = [np.pi, 0, 0]
+    poses[2] *= 4.0
+    cam = np.stack([rng.uniform(0.5, 1.5, n), rng.uniform(-.5, .5, n), rng.uniform(-.5, .5, n)], 1).astype(np.float32)
+    offsets = np.tile(np.array([512, 512, 0, 0, 0, 0, 0, 0, 0, 0], np.float32), (n, 1))
+    offsets[3] = [1920, 1920, 0, 0, 0, 0, 420, 0, 420, 0]
+    L, R = 4, 6
+    with torch.no_grad():
+        lv, lj, lc = mw.mano_layer["l"](torch.from_numpy(poses[:L]), th_betas=torch.from_numpy(betas[:L]))
+        rv, rj, rc = mw.mano_layer["r"](torch.from_numpy(poses[L:]), th_betas=torch.from_numpy(betas[L:]))
+        verts, j3d = torch.cat([lv, rv]), torch.cat([lj, rj])
+        vc = ref_utils.batch_orth_proj(verts, torch.from_numpy(cam), mode="3d", keep_dim=True)
+        pj = ref_utils.batch_orth_proj(j3d, torch.from_numpy(cam), mode="2d")[:, :, :2]
+        pjo = ref_utils.convert_kp2d_from_input_to_orgimg(pj, torch.from_numpy(offsets))
+    np.savez_compressed(os.path.join(HERE, "mano_golden.npz"), poses=poses, betas=betas, cam=cam, offsets=offsets,
+                        L=L, R=R, verts=verts.numpy(), j3d=j3d.numpy(), center=torch.cat([lc, rc]).numpy(),
+                        verts_camed=vc.numpy(), pj2d=pj.numpy(), pj2d_org=pjo.numpy())
+
+    # ------------------------------------------------------------- parser on synthetic maps
+    from acr.result_parser import ResultParser
+    rp = ResultParser()
+    cases = {}
+    for name, B, kill in (("both", 3, {}), ("no_left", 2, {"l": [0, 1]}), ("mixed", 4, {"l": [1], "r": [0, 3]}),
+                          ("none", 2, {"l": [0, 1], "r": [0, 1]}), ("far", 1, {})):
+        g = np.random.default_rng({"both": 1, "no_left": 2, "mixed": 3, "none": 4, "far": 5}[name])
+        maps = {}
+        for s in "lr":
+            cm = (g.standard_normal((B, 1, 64, 64)) * 0.1).astype(np.float32)
+            for b in range(B):
+                if b in kill.get(s, []):
+                    continue
+                y, x = g.integers(0, 64, 2)
+                if name == "far":
+                    y, x = (2, 3) if s == "l" else (60, 58)
+                cm[b, 0, y, x] = 0.9 + 0.05 * b
+                if 0 < y < 63:
+                    cm[b, 0, y + 1, x] = 0.8          # suppressed by NMS
+            maps[f"{s}_center_map"] = cm
+            maps[f"{s}_params_maps"] = g.standard_normal((B, 109, 64, 64)).astype(np.float32)
+            maps[f"{s}_prior_maps"] = (g.standard_normal((B, 106, 64, 64)) * 0.1).astype(np.float32)
+        outs = {k: torch.from_numpy(v.copy()) for k, v in maps.items()}
+        meta = {"batch_ids": torch.arange(B), "offsets": torch.zeros(B, 10), "image": torch.zeros(B, 1)}
+        o, _ = rp.parse(outs, meta, {})
+        keep = {}
+        for k in ("params_pred", "detection_flag", "reorganize_idx", "l_centers_pred", "r_centers_pred",
+                  "l_centers_conf", "r_centers_conf", "left_hand_num", "right_hand_num", "output_hand_type"):
+            keep[k] = o[k].numpy()
+        for k, v in o["params_dict"].items():
+            keep["pd_" + k] = v.numpy()
+        cases[name] = (B, keep)
+    flat = {}
+    for name, (B, keep) in cases.items():
+        flat[f"{name}__B"] = B
+        for k, v in keep.items():
+            flat[f"{name}__{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "parse_golden.npz"), **flat)
+
+    # --------------------------------------------------- full network, calibrated BN stats
+    sd = synth_state_dict(0)
+    model = ref_model.ACR().eval()
+    missing = model.load_state_dict(sd, strict=True)
+    print("state-dict keys match the reference:", missing, len(sd))
+    gi = torch.Generator().manual_seed(0)
+    calib = torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model.head_forward(model.backbone(calib))
+    model.eval()
+    stats = {k: v.numpy() for k, v in model.state_dict().items()
+             if k.endswith(("running_mean", "running_var"))}
+    np.savez_compressed(os.path.join(HERE, "bn_calib_seed0.npz"), **stats)
+    sd = synth_state_dict(0, bn_stats=stats)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+
+    gi = torch.Generator().manual_seed(123)
+    img = torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+    meta = {"image": img.clone(), "offsets": torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]] * 2),
+            "batch_ids": torch.arange(2)}
+    with torch.no_grad():
+        x = model.backbone(img)
+        heads = model.head_forward(x)
+        out = model(meta, mode="parsing", calc_loss=False)
+        # MANOWrapper.forward minus the host cv2 PnP (cam_trans is section-8f scope and the
+        # reference's INVALID_TRANS NameError fires for off-image joints, acr/utils.py:425,504)
+        Ln, Rn = int(out["left_hand_num"]), int(out["right_hand_num"])
+        pd = out["params_dict"]
+        lv, lj, _ = mw.mano_layer["l"](pd["poses"][:Ln], th_betas=pd["betas"][:Ln])
+        rv, rj, _ = mw.mano_layer["r"](pd["poses"][Ln:Ln + Rn], th_betas=pd["betas"][Ln:Ln + Rn])
+        out["verts"], out["j3d"] = torch.cat([lv, rv]), torch.cat([lj, rj])
+        pj = ref_utils.batch_orth_proj(out["j3d"], pd["cam"], mode="2d")[:, :, :2]
+        out["pj2d_org"] = ref_utils.convert_kp2d_from_input_to_orgimg(pj, out["meta_data"]["offsets"])
+    g = dict(backbone_mean=x.mean().item(), backbone_std=x.std().item(),
+             backbone_crop=x[:, :, 60:68, 60:68].numpy(),
+             segms_crop=heads["segms"][:, :, 100:108, 100:108].numpy(),
+             l_center_map=heads["l_center_map"].numpy(), r_center_map=heads["r_center_map"].numpy(),
+             l_params_crop=heads["l_params_maps"][:, :, 30:34, 30:34].numpy(),
+             r_params_crop=heads["r_params_maps"][:, :, 30:34, 30:34].numpy(),
+             l_prior_crop=heads["l_prior_maps"][:, :, 30:34, 30:34].numpy(),
+             params_pred=out["params_pred"].numpy(), detection_flag=out["detection_flag"].numpy(),
+             l_centers_pred=out["l_centers_pred"].numpy(), r_centers_pred=out["r_centers_pred"].numpy(),
+             poses=out["params_dict"]["poses"].numpy(), betas=out["params_dict"]["betas"].numpy(),
+             cam=out["params_dict"]["cam"].numpy(), verts=out["verts"].numpy(), j3d=out["j3d"].numpy(),
+             pj2d_org=out["pj2d_org"].numpy(), reorganize_idx=out["reorganize_idx"].numpy())
+    np.savez_compressed(os.path.join(HERE, "net_golden.npz"), **g)
+    for k, v in g.items():
+        print(k, getattr(v, "shape", v))
+    print("backbone mean/std", g["backbone_mean"], g["backbone_std"])
+
+
+if __name__ == "__main__":
+    main()

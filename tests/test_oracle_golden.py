@@ -1,0 +1,115 @@
+"""CPU: pin the oracle (oracle/*.py) to golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mano_ref, net_ref, parse_ref, rotation_ref
+from acr_b200.synth import load_bn_calibration, make_synthetic_mano, synth_state_dict
+
+TOL = 1e-4  # BASELINE.json north_star: 1e-4 relative fp32 tolerance
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def test_rot6d_to_axis_angle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rot_golden.npz"))
+    aa = rotation_ref.rot6d_to_angular(g["rot6d"])
+    assert aa.shape == g["aa"].shape
+    assert not np.isnan(aa).any()
+    assert np.abs(aa - g["aa"]).max() < 2e-5
+
+
+def test_rodrigues(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rot_golden.npz"))
+    r = rotation_ref.batch_rodrigues(g["aa_in"])
+    assert np.abs(r - g["rodrigues"]).max() < 1e-6
+
+
+def test_mano_forward_and_projection(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mano_golden.npz"))
+    assets = {"left": make_synthetic_mano("left"), "right": make_synthetic_mano("right")}
+    L, R = int(g["L"]), int(g["R"])
+    out = mano_ref.mano_wrapper_forward(assets, g["poses"], g["betas"], L, R, g["cam"], g["offsets"])
+    for k in ("verts", "j3d", "verts_camed", "pj2d", "pj2d_org"):
+        assert _rel(out[k], g[k]) < TOL, k
+    assert np.abs(out["verts"] - g["verts"]).max() < 2e-6   # metres
+
+
+@pytest.mark.parametrize("case", ["both", "no_left", "mixed", "none", "far"])
+def test_parse(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, "parse_golden.npz"))
+    B = int(g[f"{case}__B"])
+    maps = make_parse_case(case, B)
+    out = parse_ref.parse(maps)
+    for k in ("params_pred", "detection_flag", "reorganize_idx", "l_centers_pred", "r_centers_pred",
+              "l_centers_conf", "r_centers_conf", "left_hand_num", "right_hand_num", "output_hand_type"):
+        ref = g[f"{case}__{k}"]
+        got = np.asarray(out[k])
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        if ref.dtype.kind in "iub":
+            assert (got == ref).all(), k
+        else:
+            assert np.abs(got - ref).max() < 1e-6, k
+    for k in ("cam", "global_orient", "hand_pose", "betas", "poses"):
+        assert np.abs(out["params_dict"][k] - g[f"{case}__pd_{k}"]).max() < 2e-5, k
+
+
+def make_parse_case(name, B):
+    """Same seeded synthetic maps as tests/golden/make_golden.py."""
+    kill = {"both": {}, "no_left": {"l": [0, 1]}, "mixed": {"l": [1], "r": [0, 3]},
+            "none": {"l": [0, 1], "r": [0, 1]}, "far": {}}[name]
+    g = np.random.default_rng({"both": 1, "no_left": 2, "mixed": 3, "none": 4, "far": 5}[name])
+    maps = {}
+    for s in "lr":
+        cm = (g.standard_normal((B, 1, 64, 64)) * 0.1).astype(np.float32)
+        for b in range(B):
+            if b in kill.get(s, []):
+                continue
+            y, x = g.integers(0, 64, 2)
+            if name == "far":
+                y, x = (2, 3) if s == "l" else (60, 58)
+            cm[b, 0, y, x] = 0.9 + 0.05 * b
+            if 0 < y < 63:
+                cm[b, 0, y + 1, x] = 0.8
+        maps[f"{s}_center_map"] = cm
+        maps[f"{s}_params_maps"] = g.standard_normal((B, 109, 64, 64)).astype(np.float32)
+        maps[f"{s}_prior_maps"] = (g.standard_normal((B, 106, 64, 64)) * 0.1).astype(np.float32)
+    return maps
+
+
+def test_network_forward(golden_dir):
+    """HRNet-W32 + heads restatement vs the reference on seed-0 weights / seed-123 image."""
+    g = np.load(os.path.join(golden_dir, "net_golden.npz"))
+    sd = synth_state_dict(0, bn_stats=load_bn_calibration(0))
+    gi = torch.Generator().manual_seed(123)
+    img = torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+    torch.set_num_threads(os.cpu_count())
+    out = net_ref.net_forward(sd, img, return_backbone=True)
+    x = out["backbone"]
+    assert abs(x.mean().item() - float(g["backbone_mean"])) < 1e-4
+    assert _rel(x[:, :, 60:68, 60:68].numpy(), g["backbone_crop"]) < TOL
+    assert _rel(out["segms"][:, :, 100:108, 100:108].numpy(), g["segms_crop"]) < TOL
+    for s in "lr":
+        assert _rel(out[f"{s}_center_map"].numpy(), g[f"{s}_center_map"]) < TOL
+        assert _rel(out[f"{s}_params_maps"][:, :, 30:34, 30:34].numpy(), g[f"{s}_params_crop"]) < TOL
+    assert _rel(out["l_prior_maps"][:, :, 30:34, 30:34].numpy(), g["l_prior_crop"]) < TOL
+    # downstream: parse + MANO on the oracle's own maps reproduces the reference end to end
+    maps = {k: v.numpy() for k, v in out.items() if k.endswith(("_map", "_maps"))}
+    p = parse_ref.parse(maps)
+    assert (p["l_centers_pred"] == g["l_centers_pred"]).all() and (p["r_centers_pred"] == g["r_centers_pred"]).all()
+    assert _rel(p["params_pred"], g["params_pred"]) < TOL
+    assert np.abs(p["params_dict"]["poses"] - g["poses"]).max() < 5e-4
+    assets = {"left": make_synthetic_mano("left"), "right": make_synthetic_mano("right")}
+    L, R = int(p["left_hand_num"][0]), int(p["right_hand_num"][0])
+    offs = np.tile(np.array([512, 512, 0, 0, 0, 0, 0, 0, 0, 0], np.float32), (L + R, 1))
+    m = mano_ref.mano_wrapper_forward(assets, p["params_dict"]["poses"], p["params_dict"]["betas"], L, R,
+                                      p["params_dict"]["cam"], offs)
+    assert _rel(m["verts"], g["verts"]) < 5e-4
+    assert _rel(m["j3d"], g["j3d"]) < 5e-4
+    assert _rel(m["pj2d_org"], g["pj2d_org"]) < 5e-4
