@@ -1,0 +1,69 @@
+"""Drop-in application wrapper ``acr.main.ACR`` (reference: /root/reference/acr/main.py:24-141),
+hot path only: model -> parse -> MANO.  Rendering / visualisation / CLI loops are out of scope."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from acr.config import args
+from acr.mano_wrapper import MANOWrapper
+from acr.model import ACR as ACR_v1
+from acr.utils import justify_detection_state, load_model
+
+
+class ACR(nn.Module):
+    def __init__(self, args_set=None, state_dict=None, mano_assets=None):
+        super().__init__()
+        self.demo_cfg = {'mode': 'parsing', 'calc_loss': False}
+        cfg = vars(args() if args_set is None else args_set)
+        for k, v in cfg.items():
+            setattr(self, k, v)
+        self._build_model_(state_dict, mano_assets)
+
+    def _build_model_(self, state_dict, mano_assets):
+        model = ACR_v1().eval()
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=True)
+        else:
+            model = load_model(self.model_path, model, prefix='module.', drop_prefix='', fix_loaded=False)
+        self.model = model.cuda()
+        self.mano_regression = MANOWrapper(mano_assets).cuda()
+
+    @torch.no_grad()
+    def process_results(self, outputs):
+        outputs = self.mano_regression(outputs, outputs['meta_data'])
+        return outputs
+
+    @torch.no_grad()
+    def batch_forward(self, images_rgb_u8, offsets=None, batch_ids=None):
+        """B frames (uint8 BHWC RGB, already 512x512) -> reference-schema outputs incl. MANO."""
+        B = images_rgb_u8.shape[0]
+        if offsets is None:
+            offsets = torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]]).repeat(B, 1)
+        meta = {'image': images_rgb_u8, 'offsets': offsets,
+                'batch_ids': torch.arange(B) if batch_ids is None else batch_ids}
+        outputs = self.model(meta, **self.demo_cfg)
+        return self.process_results(outputs)
+
+    @torch.no_grad()
+    def fused_forward(self, images_rgb_u8, offsets, out=None):
+        """Sync-free pipeline: backbone + heads + parse + MANO enqueued back to back; MANO runs over
+        the worst case 2B rows and skips rows >= L+R on the device.  Returns dense buffers."""
+        B = images_rgb_u8.shape[0]
+        meta = {'image': images_rgb_u8, 'offsets': offsets, 'batch_ids': None}
+        eng, bufs = self.model.forward_dense(meta)
+        from acr_b200 import ops as _ops
+        ml, mr = self.mano_regression.models()
+        mano = _ops.mano_forward(ml, mr, bufs.poses, bufs.betas, bufs.hand_type, 1, self.mano_regression.center_idx,
+                                 bufs.cam, bufs.offsets_out, n_dev=bufs.counts[2:3])
+        return bufs, mano
+
+    @torch.no_grad()
+    def single_image_forward(self, image_rgb_u8_512, path=None):
+        meta = {'image': image_rgb_u8_512[None] if image_rgb_u8_512.dim() == 3 else image_rgb_u8_512,
+                'offsets': torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]]), 'batch_ids': torch.arange(1)}
+        outputs = self.model(meta, **self.demo_cfg)
+        outputs['detection_flag'], outputs['reorganize_idx'] = justify_detection_state(
+            outputs['detection_flag'], outputs['reorganize_idx'])
+        outputs['meta_data']['imgpath'] = [path]
+        return outputs

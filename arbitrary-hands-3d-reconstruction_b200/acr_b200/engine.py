@@ -1,0 +1,316 @@
+"""Launch-plan builder: NetSpec + state-dict -> packed weight blob, activation arena, C op list.
+
+Host-side counterpart of csrc/plan.cu.  Built once per (weights, batch size, dtype); running it is a
+single C call (``acr_b200_plan_run``) that issues every kernel of the backbone + heads.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .netspec import BN_EPS, NetSpec, Op, Tensor, build_acr_spec, conv_flops_per_image
+
+ALIGN = 1024          # arena / blob alignment (TMA global address needs 16 B; generous for swizzle)
+POOL_CHUNKS = 16
+POOL_PART_FLOATS = 256 * 32 + 64
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Blob:
+    """Append-only byte blob with aligned sub-allocations (the packed weights)."""
+
+    def __init__(self):
+        self.parts: List[bytes] = []
+        self.size = 0
+
+    def add(self, arr: np.ndarray) -> int:
+        off = _rup(self.size, 256)
+        if off > self.size:
+            self.parts.append(b"\0" * (off - self.size))
+        b = np.ascontiguousarray(arr).tobytes()
+        self.parts.append(b)
+        self.size = off + len(b)
+        return off
+
+    def tobytes(self) -> bytes:
+        return b"".join(self.parts)
+
+
+class _Arena:
+    """First-fit interval allocator over op indices (tensor liveness) -> byte offsets."""
+
+    def __init__(self):
+        self.free: List[Tuple[int, int]] = []   # (offset, size) sorted by offset
+        self.top = 0
+
+    def alloc(self, size: int) -> int:
+        size = _rup(size, ALIGN)
+        for i, (off, sz) in enumerate(self.free):
+            if sz >= size:
+                if sz == size:
+                    self.free.pop(i)
+                else:
+                    self.free[i] = (off + size, sz - size)
+                return off
+        off = self.top
+        self.top += size
+        return off
+
+    def release(self, off: int, size: int) -> None:
+        size = _rup(size, ALIGN)
+        self.free.append((off, size))
+        self.free.sort()
+        merged: List[Tuple[int, int]] = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        # give the tail back to the bump pointer
+        if merged and merged[-1][0] + merged[-1][1] == self.top:
+            self.top = merged[-1][0]
+            merged.pop()
+        self.free = merged
+
+
+class Engine:
+    """The backbone + heads of ACR as one precompiled CUDA launch plan.
+
+    ``state_dict`` uses the reference's key names (checkpoint compatible).  ``act_dtype`` is
+    torch.bfloat16 or torch.float16 (storage of activations/weights; accumulation is fp32).
+    ``debug_ref_conv`` swaps the tcgen05 conv for the CUDA-core reference kernel (tests only).
+    """
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, device, act_dtype=torch.bfloat16,
+                 input_size: int = 512, debug_ref_conv: bool = False, reuse_memory: bool = True,
+                 dry_run: bool = False):
+        self.dry_run = dry_run      # layout only (arena size, op list); used by CPU tests
+        if not dry_run and not torch.cuda.is_available():
+            raise L.AcrB200Error("Engine needs a CUDA device; there is no CPU fallback on the product path")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.batch = int(batch)
+        self.act_dtype = act_dtype
+        self.dt = {torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}[act_dtype]
+        self.np16 = np.uint16
+        self.spec: NetSpec = build_acr_spec(input_size)
+        self.input_size = input_size
+        self.flops_per_image = conv_flops_per_image(self.spec)
+        self.debug_ref_conv = debug_ref_conv
+        sd = {k: v.detach().float().cpu().numpy() for k, v in (state_dict or {}).items()
+              if v.dtype.is_floating_point}
+        self._build(sd, reuse_memory)
+
+    # ------------------------------------------------------------------ weights
+    def _pack_conv(self, sd, blob: _Blob, wkey: str, bnkey: Optional[str], has_bias: bool, cin_pad: int,
+                   cout_pad: int) -> Tuple[int, int]:
+        w = np.ascontiguousarray(sd[wkey + ".weight"], np.float32)
+        cout, cin, k, _ = w.shape
+        cb = np.ascontiguousarray(sd[wkey + ".bias"], np.float32) if has_bias else None
+        bn = [np.ascontiguousarray(sd[f"{bnkey}.{n}"], np.float32) for n in
+              ("weight", "bias", "running_mean", "running_var")] if bnkey else [None] * 4
+        wp = np.zeros((cout_pad, k * k, cin_pad), np.uint16)
+        bias = np.zeros(cout_pad, np.float32)
+        p = lambda a: None if a is None else a.ctypes.data
+        L.check(self.lib.acr_b200_pack_conv(p(w), p(cb), p(bn[0]), p(bn[1]), p(bn[2]), p(bn[3]), BN_EPS, cout, cin, k,
+                                            cout_pad, cin_pad, self.dt, wp.ctypes.data, bias.ctypes.data),
+                "pack_conv " + wkey)
+        return blob.add(wp), blob.add(bias)
+
+    # --------------------------------------------------------------------- plan
+    def _build(self, sd, reuse_memory: bool) -> None:
+        spec, B = self.spec, self.batch
+        blob = _Blob()
+        ops = spec.ops
+
+        # ---- memory geometry of every tensor
+        geo: Dict[str, dict] = {}
+
+        def geom(t: Tensor) -> dict:
+            root = t.base or t
+            if root.name not in geo:
+                if root.dtype == "u8":
+                    g = dict(stride=root.C, esz=1, dt=L.DT_U8)
+                elif root.dtype == "f32":
+                    g = dict(stride=_rup(root.C, 16), esz=4, dt=L.DT_F32)
+                else:
+                    g = dict(stride=_rup(root.C, 16), esz=2, dt=self.dt)
+                g["bytes"] = B * root.H * root.W * g["stride"] * g["esz"]
+                g["offset"] = None
+                geo[root.name] = g
+            return geo[root.name]
+
+        # flat fp32 scratch tensors of the part branch
+        part = Tensor("pool_part", POOL_CHUNKS * POOL_PART_FLOATS, 1, 1, "f32")
+        pooled = spec.tensors["pooled"]
+        pooled.C, pooled.H, pooled.W = 256 * 32, 1, 1
+        bias_img = {s: Tensor(f"{s}_bias_img", 112, 1, 1, "f32") for s in "lr"}
+        pare = {s: Tensor(f"{s}_pare", 106, 1, 1, "f32") for s in "lr"}
+        for t in [part] + list(bias_img.values()) + list(pare.values()):
+            spec.tensors[t.name] = t
+
+        # ---- expand the spec ops into launch records (python dicts first)
+        recs: List[dict] = []
+        for op in ops:
+            if op.kind == "pool":
+                recs.append(dict(kind=L.OP_POOL, out=part, ins=[op.ins[0], op.ins[1]]))
+            elif op.kind == "parthead":
+                if op.attrs["side"] == "l":   # one launch serves both sides
+                    recs.append(dict(kind=L.OP_PARTHEAD, out=pooled, ins=[part],
+                                     aux=[bias_img["l"], bias_img["r"], pare["l"], pare["r"]]))
+                s = op.attrs["side"]
+                recs.append(dict(kind=L.OP_FINALCONV, out=op.out, ins=[op.ins[1], op.ins[2], bias_img[s]], side=s))
+            elif op.kind == "coordcat":
+                recs.append(dict(kind=L.OP_COORD, out=op.out, ins=[op.ins[0]]))
+            else:
+                kind = {"stem": L.OP_STEM, "conv": L.OP_CONV_REF if self.debug_ref_conv else L.OP_CONV,
+                        "fuse": L.OP_FUSE, "bilinear2x": L.OP_BILINEAR2X}[op.kind]
+                recs.append(dict(kind=kind, out=op.out, ins=list(op.ins), attrs=op.attrs))
+        self.recs = recs
+
+        # ---- liveness (by root tensor) and arena offsets
+        keep = {"segms", "l_center_map", "r_center_map", "l_prior_maps", "r_prior_maps", "l_params_maps",
+                "r_params_maps", "pooled", "l_pare", "r_pare"}
+        keep_roots = {(spec.tensors[k].base or spec.tensors[k]).name for k in keep}
+        last_use: Dict[str, int] = {}
+        for i, r in enumerate(recs):
+            for t in r["ins"] + [r["out"]] + r.get("aux", []):
+                last_use[(t.base or t).name] = i
+        arena = _Arena()
+        for i, r in enumerate(recs):
+            for t in [r["out"]] + r.get("aux", []):
+                g = geom(t)
+                if g["offset"] is None:
+                    g["offset"] = arena.alloc(g["bytes"])
+            for t in r["ins"]:
+                g = geom(t)
+                if t.dtype != "u8":
+                    assert g["offset"] is not None, f"{t.name} read before written"
+            if reuse_memory:
+                for name, lu in last_use.items():
+                    if lu == i and name not in keep_roots and name != "image" and geo[name]["offset"] is not None \
+                            and not geo[name].get("freed"):
+                        arena.release(geo[name]["offset"], geo[name]["bytes"])
+                        geo[name]["freed"] = True
+        self.arena_bytes = max(arena.top, ALIGN)
+        for g in geo.values():
+            if g["offset"] is not None:
+                self.arena_bytes = max(self.arena_bytes, g["offset"] + _rup(g["bytes"], ALIGN))
+        self.geo = geo
+        self.n_ops = len(recs)
+        if self.dry_run:
+            return
+
+        def ctensor(t: Tensor) -> L.Tensor:
+            g = geom(t)
+            ct = L.Tensor()
+            ext = t.dtype == "u8"
+            ct.offset = 0 if ext else g["offset"] + (t.c_off * g["esz"] if t.base is not None else 0)
+            ct.C, ct.H, ct.W = t.C, t.H, t.W
+            ct.pix_stride, ct.dtype, ct.external = g["stride"], g["dt"], int(ext)
+            return ct
+
+        # ---- weights + C op records
+        f32 = lambda k: np.ascontiguousarray(sd[k], np.float32)
+        cops = (L.Op * len(recs))()
+        for i, r in enumerate(recs):
+            o = cops[i]
+            o.kind = r["kind"]
+            o.out = ctensor(r["out"])
+            o.n_in = len(r["ins"])
+            for j, t in enumerate(r["ins"]):
+                o.in_[j] = ctensor(t)
+            for j, t in enumerate(r.get("aux", [])):
+                o.aux[j] = ctensor(t)
+            a = r.get("attrs", {})
+            if r["kind"] in (L.OP_CONV, L.OP_CONV_REF):
+                x = r["ins"][0]
+                o.k, o.stride, o.relu, o.has_residual = a["k"], a["s"], int(a["relu"]), int(a["residual"])
+                o.cin_pad, o.cout_pad = _rup(x.C, 16), _rup(r["out"].C, 16)
+                o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
+            elif r["kind"] == L.OP_STEM:
+                w = f32(a["w"] + ".weight")                                   # (64,3,3,3) OIHW
+                g_, b_, m_, v_ = (f32(f"{a['bn']}.{n}") for n in ("weight", "bias", "running_mean", "running_var"))
+                sc = g_ / np.sqrt(v_ + BN_EPS)
+                wt = (w * sc[:, None, None, None]).transpose(2, 3, 1, 0).reshape(27, 64)  # [(ky,kx,ci)][co]
+                o.w_offset[0] = blob.add(wt.astype(np.float32))
+                o.w_offset[1] = blob.add((b_ - m_ * sc).astype(np.float32))
+            elif r["kind"] == L.OP_FUSE:
+                o.relu = int(a["relu"])
+                for j, sh in enumerate(a["shifts"]):
+                    o.shift[j] = sh
+            elif r["kind"] == L.OP_PARTHEAD:
+                keys = ["contact_layers.2.weight", "contact_layers.3.weight", "cam_shape_layers.1.0.weight",
+                        "cam_shape_layers.1.0.bias", "cam_shape_layers.2.weight", "cam_shape_layers.3.weight",
+                        "cam_shape_layers.2.bias", "cam_shape_layers.3.bias", "contact_layers.4.weight",
+                        "contact_layers.5.weight", "contact_layers.4.bias", "contact_layers.5.bias"]
+                for j, k in enumerate(keys):
+                    o.w_offset[j] = blob.add(f32(k).reshape(-1))
+            elif r["kind"] == L.OP_FINALCONV:
+                W = f32(f"contact_layers.{4 if r['side'] == 'l' else 5}.weight").reshape(109, 218)
+                weff = W[:, :109].copy()
+                weff[:, :3] += W[:, 109:112]
+                wt = np.zeros((112, 112), np.float32)                         # [in][out]
+                wt[:109, :109] = weff.T
+                o.w_offset[0] = blob.add(wt)
+        self.n_ops = len(recs)
+        self._cops = cops
+        self.weights = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).to(self.device)
+        self.arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)
+        plan = C.c_void_p()
+        L.check(self.lib.acr_b200_plan_create(cops, len(recs), B, self.arena.data_ptr(), self.arena_bytes,
+                                              self.weights.data_ptr(), self.weights.numel(), self.dt, C.byref(plan)),
+                "plan_create")
+        self.plan = plan
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.acr_b200_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------- run
+    def run(self, image: torch.Tensor) -> None:
+        """image: uint8 CUDA tensor (B, S, S, 3) RGB.  Asynchronous on the current stream."""
+        if not (image.is_cuda and image.dtype == torch.uint8 and image.is_contiguous()):
+            raise L.AcrB200Error("Engine.run expects a contiguous uint8 CUDA tensor (B,H,W,3)")
+        if tuple(image.shape) != (self.batch, self.input_size, self.input_size, 3):
+            raise L.AcrB200Error(f"Engine.run: expected {(self.batch, self.input_size, self.input_size, 3)}, got {tuple(image.shape)}")
+        L.check(self.lib.acr_b200_plan_run(self.plan, image.data_ptr(), L.current_stream()), "plan_run")
+
+    @property
+    def num_launches(self) -> int:
+        return int(self.lib.acr_b200_plan_num_launches(self.plan))
+
+    # ------------------------------------------------------------------ outputs
+    def view(self, name: str) -> torch.Tensor:
+        """NHWC view (B,H,W,pix_stride) of a named tensor inside the arena (no copy)."""
+        t = self.spec.tensors[name]
+        g = self.geo[(t.base or t).name]
+        tdt = {L.DT_F32: torch.float32, L.DT_BF16: torch.bfloat16, L.DT_F16: torch.float16}[g["dt"]]
+        n = self.batch * t.H * t.W * g["stride"]
+        off = g["offset"]
+        flat = self.arena[off: off + n * g["esz"]].view(tdt)
+        return flat.view(self.batch, t.H, t.W, g["stride"])
+
+    def map_nchw(self, name: str) -> torch.Tensor:
+        """fp32 NCHW copy of an output map with its logical channel count (the reference's layout)."""
+        t = self.spec.tensors[name]
+        return self.view(name)[..., : t.C].permute(0, 3, 1, 2).float().contiguous()
+
+    def parse_inputs(self) -> Dict[str, tuple]:
+        out = {}
+        for s in "lr":
+            out[f"{s}_center"] = (self.view(f"{s}_center_map"), 16)
+            out[f"{s}_params"] = (self.view(f"{s}_params_maps"), 112)
+            out[f"{s}_prior"] = (self.view(f"{s}_prior_maps"), 112)
+        return out

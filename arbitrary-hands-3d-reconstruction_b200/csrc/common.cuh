@@ -1,0 +1,63 @@
+// Shared helpers for the acr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/acr_b200.h"
+
+namespace acr {
+
+void set_error(const char* fmt, ...);
+
+#define ACR_CHECK_ARG(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      acr::set_error(__VA_ARGS__);                    \
+      return ACR_B200_EINVAL;                         \
+    }                                                 \
+  } while (0)
+
+#define ACR_CHECK_CUDA(expr)                                                           \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      acr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                        \
+      return ACR_B200_ECUDA;                                                           \
+    }                                                                                  \
+  } while (0)
+
+#define ACR_CHECK_LAUNCH() ACR_CHECK_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- 16-bit activation type helpers ------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+
+// 8 x 16-bit values <-> 8 floats through one 128-bit access
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const T* p = reinterpret_cast<const T*>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = to_f32<T>(p[i]);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  T* p = reinterpret_cast<T*>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = from_f32<T>(f[i]);
+  return u;
+}
+
+}  // namespace acr

@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol of include/acr_b200.h; host-side
+packers and the plan builder's bookkeeping behave (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from acr_b200 import lib as L
+from acr_b200.netspec import build_acr_spec, conv_flops_per_image
+from acr_b200.synth import make_synthetic_mano, synth_state_dict
+from tests.helpers import pack_conv_host, u16_to_float
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from acr_b200.build import build
+    build()
+    return L.load()
+
+
+def test_exports_match_header(lib):
+    hdr = open(os.path.join(ROOT, "include", "acr_b200.h")).read()
+    declared = set(re.findall(r"\b(acr_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/acr_b200.h but not exported"
+    assert set(L.EXPORTS) <= declared
+    assert b"sm_100a" in lib.acr_b200_version()
+
+
+def test_struct_sizes_match_c(lib):
+    # sizeof(acr_b200_tensor)=32, sizeof(acr_b200_op)=456 with the header's field order
+    assert ctypes.sizeof(L.Tensor) == 32
+    assert ctypes.sizeof(L.Op) == 4 * 2 + 32 * 9 + 8 * 12 + 4 * 6 + 4 * 4 + 4 * 2 + 4 * 4
+
+
+def test_error_reporting(lib):
+    rc = lib.acr_b200_mano_forward(None, None, None, None, None, 1, None, 4, 9, None, None, None, None, None,
+                                   None, None, None, None)
+    assert rc == -1 and b"null" in lib.acr_b200_last_error()
+    rc = lib.acr_b200_mano_forward(None, None, None, None, None, 1, None, 0, 9, None, None, None, None, None,
+                                   None, None, None, None)
+    assert rc == 0   # empty batch is a no-op (reference: "if empty, return empty", mano_wrapper.py:43)
+
+
+def test_pack_conv_folds_bn(lib):
+    g = np.random.default_rng(0)
+    w = g.standard_normal((5, 7, 3, 3)).astype(np.float32)
+    cb = g.standard_normal(5).astype(np.float32)
+    bn = [g.random(5).astype(np.float32) + 0.5, g.standard_normal(5).astype(np.float32),
+          g.standard_normal(5).astype(np.float32), g.random(5).astype(np.float32) + 0.5]
+    wp, bias = pack_conv_host(w, cb, bn, 16, 16, L.DT_BF16)
+    sc = bn[0] / np.sqrt(bn[3] + 1e-5)
+    ref_w = (w * sc[:, None, None, None]).transpose(0, 2, 3, 1).reshape(5, 9, 7)    # [co][tap][ci]
+    got = u16_to_float(wp, L.DT_BF16).numpy().reshape(16, 9, 16)
+    assert np.abs(got[:5, :, :7] - ref_w).max() <= np.abs(ref_w).max() * 2 ** -8
+    assert (got[5:] == 0).all() and (got[:, :, 7:] == 0).all()
+    assert np.allclose(bias[:5], bn[1] - bn[2] * sc + cb * sc, atol=1e-6) and (bias[5:] == 0).all()
+
+
+def test_mano_pack_model_host(lib):
+    a = make_synthetic_mano("left")
+    n = lib.acr_b200_mano_model_floats()
+    out = np.zeros(n, np.float32)
+    arrs = [np.ascontiguousarray(a[k], np.float32) for k in
+            ("shapedirs", "posedirs", "v_template", "J_regressor", "weights", "hands_mean")]
+    assert lib.acr_b200_mano_pack_model(*[x.ctypes.data for x in arrs], 1, out.ctypes.data) == 0
+    NVP = 784
+    dirs = out[:145 * 3 * NVP].reshape(145, 3, NVP)
+    assert np.array_equal(dirs[:135, :, :778], a["posedirs"].transpose(2, 1, 0))
+    sd = a["shapedirs"].copy()
+    sd[:, 0, :] *= -1
+    assert np.array_equal(dirs[135:, :, :778], sd.transpose(2, 1, 0))
+    jt = out[145 * 3 * NVP + 3 * NVP + 16 * NVP:][:48].reshape(16, 3)
+    assert np.allclose(jt, a["J_regressor"] @ a["v_template"], atol=1e-7)
+
+
+def test_spec_matches_reference_counts():
+    spec = build_acr_spec()
+    assert len(spec.params) == 2067                       # 2067 tensors
+    n = sum(int(np.prod(s)) for s, _ in spec.params.values())
+    assert abs(n - 30.31e6) < 0.2e6
+    assert abs(conv_flops_per_image(spec) / 1e9 - 102.12) < 0.05
+    sd = synth_state_dict(3)
+    assert list(sd.keys()) == list(spec.params.keys())
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from acr_b200 import ops
+    with pytest.raises(L.AcrB200Error):
+        ops.rot6d_to_aa(torch.zeros(2, 6))
+    from acr_b200.engine import Engine
+    with pytest.raises(L.AcrB200Error):
+        Engine({}, 1, "cpu")

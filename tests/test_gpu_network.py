@@ -1,0 +1,115 @@
+"""GPU parity: the whole launch plan (backbone + heads), the fused pipeline and the drop-in API vs the
+oracle / the reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from acr_b200.synth import load_bn_calibration, synth_state_dict
+    return synth_state_dict(0, bn_stats=load_bn_calibration(0))
+
+
+@pytest.fixture(scope="module")
+def image():
+    gi = torch.Generator().manual_seed(123)
+    return torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+
+
+@pytest.fixture(scope="module")
+def oracle_out(sd, image):
+    from oracle import net_ref
+    torch.set_num_threads(os.cpu_count())
+    return net_ref.net_forward(sd, image, return_backbone=True)
+
+
+def _engine_maps(sd, image, ref_conv, dtype=torch.bfloat16):
+    from acr_b200.engine import Engine
+    eng = Engine(sd, image.shape[0], "cuda", dtype, debug_ref_conv=ref_conv)
+    eng.run(image.cuda())
+    torch.cuda.synchronize()
+    names = ["l_center_map", "r_center_map", "l_params_maps", "r_params_maps", "l_prior_maps", "r_prior_maps", "segms"]
+    out = {n: eng.map_nchw(n).cpu() for n in names}
+    out["backbone"] = eng.view("feat32")[..., :32].permute(0, 3, 1, 2).float().cpu()
+    out["pooled"] = eng.view("pooled").view(image.shape[0], 256, 32).cpu()
+    return eng, out
+
+
+def _cmp(out, ref, tol):
+    worst = {}
+    for k in ("backbone", "segms", "l_center_map", "r_center_map", "l_params_maps", "r_params_maps",
+              "l_prior_maps", "r_prior_maps", "pooled"):
+        worst[k] = rel_err(out[k].numpy(), ref[k].numpy())
+    print("rel errors:", {k: f"{v:.3e}" for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v < tol, (k, v)
+    return worst
+
+
+def test_plan_refconv_vs_oracle(sd, image, oracle_out):
+    """Everything except the tensor-core conv (stem, fuse, bilinear, pooling, part head, plan wiring)."""
+    _, out = _engine_maps(sd, image, ref_conv=True)
+    _cmp(out, oracle_out, 3e-2)     # bf16 storage through ~80 sequential layers vs fp32 reference
+
+
+def test_plan_tcgen05_vs_oracle(sd, image, oracle_out):
+    _, out = _engine_maps(sd, image, ref_conv=False)
+    _cmp(out, oracle_out, 3e-2)
+
+
+def test_plan_tcgen05_matches_refconv(sd, image):
+    """Same rounding points, different conv engine: must agree to bf16 round-off."""
+    _, a = _engine_maps(sd, image, ref_conv=False)
+    _, b = _engine_maps(sd, image, ref_conv=True)
+    for k in a:
+        assert rel_err(a[k].numpy(), b[k].numpy()) < 1.5e-2, k
+
+
+def test_plan_fp16_vs_oracle(sd, image, oracle_out):
+    _, out = _engine_maps(sd, image, ref_conv=False, dtype=torch.float16)
+    _cmp(out, oracle_out, 1e-2)
+
+
+def test_dropin_api_end_to_end(sd, image):
+    """acr.main.ACR -> acr.model.ACR.forward -> MANOWrapper.forward against (a) the oracle run on the
+    engine's own maps (fp32 tail at 1e-4) and (b) the reference goldens (bf16 backbone tolerance)."""
+    from acr.main import ACR
+    from acr_b200.synth import make_synthetic_mano
+    from oracle import mano_ref, parse_ref
+    assets = {"left": make_synthetic_mano("left"), "right": make_synthetic_mano("right")}
+    app = ACR(state_dict=sd, mano_assets=assets)
+    out = app.batch_forward(image)
+    maps = {k: out[k].cpu().numpy() for k in ("l_center_map", "r_center_map", "l_params_maps", "r_params_maps",
+                                              "l_prior_maps", "r_prior_maps")}
+    p = parse_ref.parse(maps)
+    N = p["params_pred"].shape[0]
+    assert out["params_pred"].shape[0] == N
+    assert (out["reorganize_idx"].cpu().numpy() == p["reorganize_idx"]).all()
+    assert (out["l_centers_pred"].cpu().numpy() == p["l_centers_pred"]).all()
+    assert (out["r_centers_pred"].cpu().numpy() == p["r_centers_pred"]).all()
+    assert np.abs(out["params_pred"].cpu().numpy() - p["params_pred"]).max() < 1e-5
+    L_, R_ = int(p["left_hand_num"][0]), int(p["right_hand_num"][0])
+    offs = np.tile(np.array([512, 512, 0, 0, 0, 0, 0, 0, 0, 0], np.float32), (N, 1))
+    m = mano_ref.mano_wrapper_forward(assets, p["params_dict"]["poses"], p["params_dict"]["betas"], L_, R_,
+                                      p["params_dict"]["cam"], offs)
+    assert rel_err(out["verts"].cpu().numpy(), m["verts"]) < 1e-4
+    assert rel_err(out["j3d"].cpu().numpy(), m["j3d"]) < 1e-4
+    assert rel_err(out["pj2d_org"].cpu().numpy(), m["pj2d_org"]) < 1e-4
+    # (b) reference goldens: same centres, outputs within the 16-bit backbone's tolerance
+    g = np.load(os.path.join(GOLDEN, "net_golden.npz"))
+    assert (out["l_centers_pred"].cpu().numpy() == g["l_centers_pred"]).all()
+    assert (out["r_centers_pred"].cpu().numpy() == g["r_centers_pred"]).all()
+    assert rel_err(out["params_pred"].cpu().numpy(), g["params_pred"]) < 5e-2
+    assert out["verts"].shape == g["verts"].shape
+    # fused sync-free pipeline gives the same rows
+    bufs, mano = app.fused_forward(image.cuda(), torch.from_numpy(offs[:2]).cuda())
+    torch.cuda.synchronize()
+    assert int(bufs.counts[2]) == N
+    assert torch.equal(mano["verts"][:N], out["verts"])
