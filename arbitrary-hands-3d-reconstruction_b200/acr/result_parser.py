@@ -26,18 +26,18 @@ class ResultParser(nn.Module):
         if (args().prior_mode, args().inter_prior, args().Rot_type, self.map_size) != ('cross', True, '6D', 64):
             raise ValueError("only prior_mode='cross', inter_prior=True, Rot_type='6D', centermap_size=64 "
                              "(the reference's shipped configuration) are supported")
-        self._bufs = {}
+        self._pbufs = {}
 
-    def _buffers(self, B, device):
+    def _parse_buffers(self, B, device):
         key = (B, str(device))
-        if key not in self._bufs:
-            self._bufs[key] = _ops.ParseBuffers(B, device)
-        return self._bufs[key]
+        if key not in self._pbufs:
+            self._pbufs[key] = _ops.ParseBuffers(B, device)
+        return self._pbufs[key]
 
     # ------------------------------------------------------------------ kernels
     def launch(self, maps, B, meta_data, device):
         """Enqueue the parse kernels; returns the worst-case buffers (no sync)."""
-        bufs = self._buffers(B, device)
+        bufs = self._parse_buffers(B, device)
         ids = meta_data.get('batch_ids') if meta_data is not None else None
         offs = meta_data.get('offsets') if meta_data is not None else None
         _ops.parse_maps(maps, B, bufs, ids, offs, args().centermap_conf_thresh)

@@ -90,7 +90,8 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, device, act_dtype=torch.bfloat16,
                  input_size: int = 512, debug_ref_conv: bool = False, reuse_memory: bool = True,
-                 dry_run: bool = False):
+                 dry_run: bool = False, keep_extra=()):
+        self.keep_extra = tuple(keep_extra)   # extra tensor names kept alive after the run (tests)
         self.dry_run = dry_run      # layout only (arena size, op list); used by CPU tests
         if not dry_run and not torch.cuda.is_available():
             raise L.AcrB200Error("Engine needs a CUDA device; there is no CPU fallback on the product path")
@@ -178,6 +179,7 @@ class Engine:
         # ---- liveness (by root tensor) and arena offsets
         keep = {"segms", "l_center_map", "r_center_map", "l_prior_maps", "r_prior_maps", "l_params_maps",
                 "r_params_maps", "pooled", "l_pare", "r_pare"}
+        keep |= set(self.keep_extra)
         keep_roots = {(spec.tensors[k].base or spec.tensors[k]).name for k in keep}
         last_use: Dict[str, int] = {}
         for i, r in enumerate(recs):
@@ -286,6 +288,14 @@ class Engine:
         if tuple(image.shape) != (self.batch, self.input_size, self.input_size, 3):
             raise L.AcrB200Error(f"Engine.run: expected {(self.batch, self.input_size, self.input_size, 3)}, got {tuple(image.shape)}")
         L.check(self.lib.acr_b200_plan_run(self.plan, image.data_ptr(), L.current_stream()), "plan_run")
+
+    def profile(self, image: torch.Tensor) -> Dict[int, Tuple[float, int]]:
+        """One serialised, event-bracketed pass: {op kind: (device ms, launches)}."""
+        ms = np.zeros(16, np.float32)
+        cnt = np.zeros(16, np.int32)
+        L.check(self.lib.acr_b200_plan_profile(self.plan, image.data_ptr(), L.current_stream(), ms.ctypes.data,
+                                               cnt.ctypes.data), "plan_profile")
+        return {k: (float(ms[k]), int(cnt[k])) for k in range(16) if cnt[k]}
 
     @property
     def num_launches(self) -> int:

@@ -49,7 +49,7 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTS = ["acr_b200_last_error", "acr_b200_version", "acr_b200_mano_model_floats", "acr_b200_mano_pack_model",
            "acr_b200_mano_forward", "acr_b200_rot6d_to_aa", "acr_b200_rodrigues", "acr_b200_parse",
-           "acr_b200_plan_create", "acr_b200_plan_run", "acr_b200_plan_num_launches", "acr_b200_plan_destroy",
+           "acr_b200_plan_create", "acr_b200_plan_run", "acr_b200_plan_profile", "acr_b200_plan_num_launches", "acr_b200_plan_destroy",
            "acr_b200_run_op", "acr_b200_pack_conv"]
 
 
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.acr_b200_plan_create.argtypes = [C.POINTER(Op), i32, i32, vp, C.c_size_t, vp, C.c_size_t, i32,
                                          C.POINTER(vp)]
     lib.acr_b200_plan_run.argtypes = [vp, vp, vp]
+    lib.acr_b200_plan_profile.argtypes = [vp, vp, vp, vp, vp]
     lib.acr_b200_plan_num_launches.argtypes = [vp]
     lib.acr_b200_plan_destroy.argtypes = [vp]
     lib.acr_b200_plan_destroy.restype = None

@@ -215,6 +215,33 @@ extern "C" int acr_b200_plan_run(acr_b200_plan* p, const void* image, void* stre
   return ACR_B200_OK;
 }
 
+extern "C" int acr_b200_plan_profile(acr_b200_plan* p, const void* image, void* stream, float* ms_by_kind,
+                                     int32_t* n_by_kind) {
+  ACR_CHECK_ARG(p && image && ms_by_kind && n_by_kind, "plan_profile: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = (int)p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) ACR_CHECK_CUDA(cudaEventCreate(&e));
+  ACR_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  int rc = ACR_B200_OK;
+  for (int i = 0; i < n && rc == ACR_B200_OK; ++i) {
+    rc = run_one(p->ops[i], p->batch, p->arena, p->weights, static_cast<const char*>(image), p->act_dtype, p->tc[i], st);
+    if (rc == ACR_B200_OK && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = ACR_B200_ECUDA;
+  }
+  if (rc == ACR_B200_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error("plan_profile: sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = ACR_B200_ECUDA; }
+  if (rc == ACR_B200_OK) {
+    for (int k = 0; k < 16; ++k) { ms_by_kind[k] = 0.f; n_by_kind[k] = 0; }
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      const int k = p->ops[i].kind & 15;
+      ms_by_kind[k] += ms; n_by_kind[k] += 1;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
 extern "C" int acr_b200_plan_num_launches(const acr_b200_plan* p) { return p ? (int)p->ops.size() : 0; }
 
 extern "C" void acr_b200_plan_destroy(acr_b200_plan* p) {

@@ -9,6 +9,12 @@
 
 namespace acr {
 
+// separately rounded products/sums (no FMA contraction), like the reference's element-wise ATen
+// kernels: keeps the Gram-Schmidt residual of near-degenerate 6D inputs identical to the reference's
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
 __device__ __forceinline__ void rodrigues(float ax, float ay, float az, float* R) {
   // angle = || aa + 1e-8 ||, axis = aa / angle, q = [cos(a/2), sin(a/2) axis], q /= ||q||
   const float bx = ax + 1e-8f, by = ay + 1e-8f, bz = az + 1e-8f;
@@ -31,13 +37,16 @@ __device__ __forceinline__ void rot6d_to_aa(const float* __restrict__ r6, float*
   const float a1x = r6[0], a1y = r6[2], a1z = r6[4];
   const float a2x = r6[1], a2y = r6[3], a2z = r6[5];
   // b1 = a1 / max(||a1||, 1e-6)
-  float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-6f);
+  float n1 = fmaxf(sqrtf(dot3_rn(a1x, a1y, a1z, a1x, a1y, a1z)), 1e-6f);
   const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
-  const float d = b1x * a2x + b1y * a2y + b1z * a2z;
-  const float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
-  float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-6f);
+  const float d = dot3_rn(b1x, b1y, b1z, a2x, a2y, a2z);
+  const float ux = __fsub_rn(a2x, __fmul_rn(d, b1x)), uy = __fsub_rn(a2y, __fmul_rn(d, b1y)),
+              uz = __fsub_rn(a2z, __fmul_rn(d, b1z));
+  float n2 = fmaxf(sqrtf(dot3_rn(ux, uy, uz, ux, uy, uz)), 1e-6f);
   const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
-  const float b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
+  const float b3x = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y)),
+              b3y = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z)),
+              b3z = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
   // R = [b1 b2 b3] (columns); the quaternion selection runs on t = R^T, i.e. t(i,j) = R(j,i)
   //   t00=b1x t01=b1y t02=b1z / t10=b2x t11=b2y t12=b2z / t20=b3x t21=b3y t22=b3z
   const float t00 = b1x, t01 = b1y, t02 = b1z, t10 = b2x, t11 = b2y, t12 = b2z, t20 = b3x, t21 = b3y, t22 = b3z;

@@ -39,7 +39,7 @@ class ManoLayer(Module):
         smpl_data = asset if asset is not None else get_asset(mano_root, side)
         self.smpl_data = smpl_data
         hands_components = np.asarray(smpl_data['hands_components'], np.float32)
-        T = lambda a, dt=np.float32: torch.from_numpy(np.ascontiguousarray(np.asarray(a), dt))
+        T = lambda a, dt=np.float32: torch.from_numpy(np.array(a, dtype=dt, copy=True, order='C'))  # copies, like torch.Tensor(a)
         self.register_buffer('th_betas', T(smpl_data['betas']).unsqueeze(0))
         self.register_buffer('th_shapedirs', T(smpl_data['shapedirs']))
         self.register_buffer('th_posedirs', T(smpl_data['posedirs']))

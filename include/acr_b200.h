@@ -173,6 +173,11 @@ int acr_b200_plan_create(const acr_b200_op* ops, int n_ops, int batch, void* are
                          int act_dtype, acr_b200_plan** plan_out);
 /* Run the plan on `stream`: `image` is the external uint8 (batch,512,512,3) input.        */
 int acr_b200_plan_run(acr_b200_plan* plan, const void* image, void* stream);
+/* Like plan_run, but brackets every launch with CUDA events on `stream` (serialising the plan) and
+ * accumulates device milliseconds / launch counts per op kind into ms_by_kind[16] / n_by_kind[16]
+ * (host arrays, indexed by ACR_OP_*).  Synchronises `stream`.  Used by bench.py for the roofline. */
+int acr_b200_plan_profile(acr_b200_plan* plan, const void* image, void* stream, float* ms_by_kind,
+                          int32_t* n_by_kind);
 /* Number of kernel launches one plan_run issues (for bench.py's gpu_launches).            */
 int acr_b200_plan_num_launches(const acr_b200_plan* plan);
 void acr_b200_plan_destroy(acr_b200_plan* plan);
