@@ -16,10 +16,14 @@
 //   * B operand: packed weights [cout_pad][taps*cin_pad] (BN folded), one 2-D TMA box {CK, cout_pad}.
 //   * Both land in shared memory in the canonical K-major swizzled layout (128B / 64B / 32B swizzle
 //     for CK = 64 / 32 / 16) that UMMA shared-memory descriptors address directly.
+//   * 3x3 stride-1 convs use "patch mode": for each kx one 18(y) x 8(x) box is loaded and the three
+//     ky taps are three UMMA descriptors 8 rows (= one swizzle atom) apart inside it, so the input
+//     is pulled through L2 3.4x instead of 9x.
+//   * persistent CTAs (one per SM) loop over tiles; weights stay resident in shared memory when they
+//     fit (all 32/64-channel layers), otherwise they stream through their own mbarrier ring.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread issues tcgen05.mma, fp32 accumulators
-//     in TMEM), warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) (ReLU) -> 16-bit / fp32 NHWC).
-//   * a NUM_STAGES-deep mbarrier ring decouples TMA from the tensor pipe; several CTAs are resident
-//     per SM (TMEM columns and smem permitting) so one CTA's epilogue overlaps another's main loop.
+//     in TMEM, double buffered), warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) (ReLU) ->
+//     16-bit / fp32 NHWC) overlapping the next tile's main loop.
 #include <cuda.h>
 
 #include "ops.cuh"
@@ -54,6 +58,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
              threadIdx.x, bar, parity);
       __trap();
     }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -119,8 +126,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 }
 
 // ------------------------------------------------------------------------------------ kernel
-constexpr int TILE_Y = 16, TILE_X = 8, TILE_M = 128;
-constexpr int TC_THREADS = 192;
+// Measured on B200 (tools/tma_bench.cu, 148 CTAs): a 4-D TMA box costs ~620 clk per SM whatever its
+// size (4 KB .. 72 KB), a 2-D box ~320 clk.  So the CTA works on 16x16-pixel super-tiles: ONE box per
+// (channel chunk, kx) feeds two M=128 UMMA tiles (left / right 8 columns) and three ky taps.
+constexpr int TILE_Y = 16, TILE_X = 16, HALF_X = 8, TILE_M = 128;
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SMEM_BUDGET = 224 * 1024;
 
 struct ConvTcParams {
   CUtensorMap tmA[4];
@@ -128,47 +140,60 @@ struct ConvTcParams {
   const float* bias;
   const void* res;
   void* out;
-  int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, num_stages, tmem_cols;
-  int tiles_x, Ho, Wo, out_stride, res_stride;
+  int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32;
+  int patch_mode, b_resident, SA, SB;
+  uint32_t a_stage_bytes, b_block_bytes, b_region_bytes;
+  int tmem_cols, acc_stride, nbuf;
+  int tiles_x, tiles_per_img, total_tiles, Ho, Wo, out_stride, res_stride;
   uint32_t idesc;
 };
 
 template <int CK>
 struct SwizzleCfg {
   static constexpr uint32_t kRowBytes = CK * 2;
-  static constexpr uint32_t kSBO = 8 * kRowBytes;  // 8-row core-matrix group
+  static constexpr uint32_t kAtom = 8 * kRowBytes;          // 8 pixels of one image row = one swizzle atom
+  static constexpr uint32_t kSBO_A = TILE_X * kRowBytes;    // next image row of the 16-wide box
   static constexpr uint32_t kLayout = CK == 64 ? 2u : (CK == 32 ? 4u : 6u);
-  static constexpr uint32_t kABytes = TILE_M * kRowBytes;
 };
 
 template <int CK, typename T>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using Cfg = SwizzleCfg<CK>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
-  const uint32_t b_bytes = (uint32_t)P.npad * Cfg::kRowBytes;
-  const uint32_t stage_bytes = (Cfg::kABytes + b_bytes + 1023u) & ~1023u;
-  const int S = P.num_stages;
-  const uint32_t bar_base = base + (uint32_t)S * stage_bytes;  // full[S], empty[S], tmem_full, tmem_ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * S + 1);
+  const int SA = P.SA, SB = P.SB;
+  const uint32_t b_base = base;
+  const uint32_t a_base = base + P.b_region_bytes;
+  const uint32_t bias_base = a_base + (uint32_t)SA * P.a_stage_bytes;   // fp32 bias[npad] (<= 1 KB)
+  const uint32_t bar_base = bias_base + 1024u;
+  // barrier map: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] bres tmem_full[2] tmem_empty[2] | tmem_ptr
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * SA + 2 * SB);
+  auto tmem_full = [&](int b) { return bres_bar + 8u * (1 + b); };
+  auto tmem_empty = [&](int b) { return bres_bar + 8u * (3 + b); };
+  const uint32_t tmem_ptr_addr = bres_bar + 8u * 5;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ty = blockIdx.x / P.tiles_x, tx = blockIdx.x % P.tiles_x, n = blockIdx.y;
-  const int y0 = ty * TILE_Y, x0 = tx * TILE_X;
-  const int kiters = P.taps * P.cchunks;
+  const int nA = P.patch_mode ? P.cchunks * 3 : P.taps * P.cchunks;  // A loads per super-tile
+  const int nsub = P.patch_mode ? 3 : 1;                             // taps served by one A load
+  const int nbuf = P.nbuf;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    mbar_init(bres_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS); }
     fence_barrier_init();
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
   }
+  for (int i = threadIdx.x; i < P.npad; i += TC_THREADS) s_bias[i] = P.bias[i];
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -178,89 +203,174 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int tap = it / P.cchunks, cc = it % P.cchunks;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), Cfg::kABytes + b_bytes);
-        const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
-        const uint32_t b_dst = a_dst + Cfg::kABytes;
-        int view = 0, dy = 0, dx = 0;
-        if (P.ksz == 3) {
-          const int ky = tap / 3, kx = tap % 3;
-          if (P.stride == 1) { dy = ky - 1; dx = kx - 1; }
-          else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
-            const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
-            dy = (ky == 0) ? -1 : 0; dx = (kx == 0) ? -1 : 0;
-            view = py * 2 + px;
+      if (P.b_resident) {  // whole weight tensor once per CTA
+        const int nblk = P.taps * P.cchunks;
+        mbar_expect_tx(bres_bar, (uint32_t)nblk * P.b_block_bytes);
+        for (int i = 0; i < nblk; ++i)
+          tma_load_2d(b_base + (uint32_t)i * P.b_block_bytes, &P.tmB, bres_bar, (i / P.cchunks) * P.cin_pad + (i % P.cchunks) * CK, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
+        const int y0 = (rem / P.tiles_x) * TILE_Y, x0 = (rem % P.tiles_x) * TILE_X;
+        for (int a = 0; a < nA; ++a) {
+          int cc, view = 0, dy = 0, dx = 0, tap0;
+          if (P.patch_mode) {           // one 18x16 box per (channel chunk, kx); rows y0-1 .. y0+16
+            cc = a / 3; const int kx = a % 3;
+            dy = -1; dx = kx - 1; tap0 = kx;
+          } else {
+            const int tap = a / P.cchunks; cc = a % P.cchunks; tap0 = tap;
+            if (P.ksz == 3) {
+              const int ky = tap / 3, kx = tap % 3;
+              if (P.stride == 1) { dy = ky - 1; dx = kx - 1; }
+              else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
+                const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
+                dy = (ky == 0) ? -1 : 0; dx = (kx == 0) ? -1 : 0;
+                view = py * 2 + px;
+              }
+            }
+          }
+          mbar_wait(emptyA(sa), pha ^ 1u);
+          mbar_expect_tx(fullA(sa), P.a_stage_bytes);
+          tma_load_4d(a_base + (uint32_t)sa * P.a_stage_bytes, &P.tmA[view], fullA(sa), cc * CK, x0 + dx, y0 + dy, n);
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+          if (!P.b_resident) {
+            for (int sub = 0; sub < nsub; ++sub) {
+              const int tap = P.patch_mode ? sub * 3 + tap0 : tap0;
+              mbar_wait(emptyB(sb), phb ^ 1u);
+              mbar_expect_tx(fullB(sb), P.b_block_bytes);
+              tma_load_2d(b_base + (uint32_t)sb * P.b_block_bytes, &P.tmB, fullB(sb), tap * P.cin_pad + cc * CK, 0);
+              if (++sb == SB) { sb = 0; phb ^= 1u; }
+            }
           }
         }
-        tma_load_4d(a_dst, &P.tmA[view], full_bar(s), cc * CK, x0 + dx, y0 + dy, n);
-        tma_load_2d(b_dst, &P.tmB, full_bar(s), tap * P.cin_pad + cc * CK, 0);
-        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < kiters; ++it) {
-        mbar_wait(full_bar(s), ph);
+      if (P.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;   // how often this buffer was used before
+        mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator pair
         tc_fence_after();
-        const uint32_t a_src = base + (uint32_t)s * stage_bytes;
-        const uint32_t b_src = a_src + Cfg::kABytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 2 * P.acc_stride);
+        uint32_t accum = 0;
+        for (int a = 0; a < nA; ++a) {
+          int cc, tap0;
+          if (P.patch_mode) { cc = a / 3; tap0 = a % 3; } else { tap0 = a / P.cchunks; cc = a % P.cchunks; }
+          mbar_wait(fullA(sa), pha);
+          tc_fence_after();
+          const uint32_t a_src = a_base + (uint32_t)sa * P.a_stage_bytes;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int tap = P.patch_mode ? sub * 3 + tap0 : tap0;
+            uint32_t b_src;
+            if (P.b_resident) b_src = b_base + (uint32_t)(tap * P.cchunks + cc) * P.b_block_bytes;
+            else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_src = b_base + (uint32_t)sb * P.b_block_bytes; }
+            const uint32_t a_tap = a_src + (uint32_t)sub * Cfg::kSBO_A;  // ky shift = one 16-pixel box row
 #pragma unroll
-        for (int ks = 0; ks < CK / 16; ++ks) {
-          const uint64_t da = make_smem_desc(a_src + ks * 32, Cfg::kSBO, Cfg::kLayout);
-          const uint64_t db = make_smem_desc(b_src + ks * 32, Cfg::kSBO, Cfg::kLayout);
-          umma_f16(tmem_base, da, db, P.idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            for (int h = 0; h < 2; ++h) {                                // left / right 8 output columns
+#pragma unroll
+              for (int ks = 0; ks < CK / 16; ++ks)
+                umma_f16(d_tmem + (uint32_t)(h * P.acc_stride),
+                         make_smem_desc(a_tap + h * Cfg::kAtom + ks * 32, Cfg::kSBO_A, Cfg::kLayout),
+                         make_smem_desc(b_src + ks * 32, Cfg::kAtom, Cfg::kLayout), P.idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+            }
+            accum = 1u;  // only the very first k-step of each accumulator overwrites
+            if (!P.b_resident) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
+          }
+          umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
         }
-        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
-        if (++s == S) { s = 0; ph ^= 1u; }
+        umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ========================================================================= epilogue
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;         // which half (accumulator) of the super-tile
     const int r = q * 32 + lane;
-    const int oy = y0 + (r >> 3), ox = x0 + (r & 7);
-    const size_t pix = ((size_t)n * P.Ho + oy) * P.Wo + ox;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride : nullptr;
-    for (int c0 = 0; c0 < P.npad; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      float f[16];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = nbuf == 2 ? (it & 1) : 0;
+      const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
+      const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
+      const int oy = (rem / P.tiles_x) * TILE_Y + (r >> 3), ox = (rem % P.tiles_x) * TILE_X + h * HALF_X + (r & 7);
+      const size_t pix = ((size_t)n * P.Ho + oy) * P.Wo + ox;
+      const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride : nullptr;
+      uint4 rr[4][2];
+      if (resp) {   // prefetch the first 64 residual channels while the MMAs are still running
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + __ldg(P.bias + c0 + i);
-      if (resp) {
-        float rr[16];
-        unpack8<T>(*reinterpret_cast<const uint4*>(resp + c0), rr);
-        unpack8<T>(*reinterpret_cast<const uint4*>(resp + c0 + 8), rr + 8);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] += rr[i];
+        for (int c = 0; c < 4; ++c)
+          if (c * 16 < P.npad) {
+            rr[c][0] = *reinterpret_cast<const uint4*>(resp + c * 16);
+            rr[c][1] = *reinterpret_cast<const uint4*>(resp + c * 16 + 8);
+          }
       }
-      if (P.relu) {
+      mbar_wait(tmem_full(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
+      for (int g0 = 0; g0 < P.npad; g0 += 64) {
+        const int nch = min(4, (P.npad - g0) >> 4);  // 16-column chunks in this group (warp-uniform)
+        uint32_t v[4][16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      if (P.out_f32) {
-        float* o = reinterpret_cast<float*>(P.out) + pix * P.out_stride + c0;
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) tmem_ld16(t_row + (uint32_t)(g0 + c * 16), v[c]);
+        if (resp && g0 > 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      } else {
-        T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + c0;
-        reinterpret_cast<uint4*>(o)[0] = pack8<T>(f);
-        reinterpret_cast<uint4*>(o)[1] = pack8<T>(f + 8);
+          for (int c = 0; c < 4; ++c)
+            if (c < nch) {
+              rr[c][0] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16);
+              rr[c][1] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16 + 8);
+            }
+        }
+        tmem_ld_wait();
+        if (g0 + 64 >= P.npad) {  // all TMEM reads of this tile done: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(buf));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c >= nch) continue;
+          const int c0 = g0 + c * 16;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);
+            f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
+          }
+          if (resp) {
+            float x[16];
+            unpack8<T>(rr[c][0], x);
+            unpack8<T>(rr[c][1], x + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += x[i];
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (P.out_f32) {
+            float* o = reinterpret_cast<float*>(P.out) + pix * P.out_stride + c0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + c0;
+            reinterpret_cast<uint4*>(o)[0] = pack8<T>(f);
+            reinterpret_cast<uint4*>(o)[1] = pack8<T>(f + 8);
+          }
+        }
       }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -271,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // --------------------------------------------------------------------------------- host side
 struct ConvTcPlan {
   ConvTcParams p;
-  int ck, act_dtype, batch, tiles;
+  int ck, act_dtype, grid;
   size_t smem;
 };
 
@@ -291,6 +401,15 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int encode(CUtensorMap* m, int act_dtype, int rank, const void* ptr, const cuuint64_t* dims,
                   const cuuint64_t* strides, const cuuint32_t* box, int ck) {
   PFN_encodeTiled fn = get_encode();
@@ -305,7 +424,7 @@ static int encode(CUtensorMap* m, int act_dtype, int rank, const void* ptr, cons
 }
 
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
-  ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x8 tile", a.out.H, a.out.W);
+  ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x16 super-tile", a.out.H, a.out.W);
   ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 256,
                 "conv_tc: channel alignment");
   ACR_CHECK_ARG(a.in.dtype == act_dtype, "conv_tc: input dtype mismatch");
@@ -313,7 +432,9 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   const int ck = (a.cin_pad % 64 == 0) ? 64 : ((a.cin_pad % 32 == 0) ? 32 : 16);
   ConvTcPlan* pl = new ConvTcPlan();
   ConvTcParams& p = pl->p;
-  pl->ck = ck; pl->act_dtype = act_dtype; pl->batch = a.batch;
+  pl->ck = ck; pl->act_dtype = act_dtype;
+  p.patch_mode = (a.k == 3 && a.stride == 1) ? 1 : 0;
+  const cuuint32_t box_rows = p.patch_mode ? TILE_Y + 2 : TILE_Y;
   const cuuint64_t esz = 2;
   const cuuint64_t dim0 = (cuuint64_t)(a.cin_pad < a.in.pix_stride ? a.cin_pad : a.in.pix_stride);
   int rc = ACR_B200_OK;
@@ -321,7 +442,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     cuuint64_t dims[4] = {dim0, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.batch};
     cuuint64_t str[3] = {(cuuint64_t)a.in.pix_stride * esz, (cuuint64_t)a.in.W * a.in.pix_stride * esz,
                          (cuuint64_t)a.in.H * a.in.W * a.in.pix_stride * esz};
-    cuuint32_t box[4] = {(cuuint32_t)ck, TILE_X, TILE_Y, 1};
+    cuuint32_t box[4] = {(cuuint32_t)ck, TILE_X, box_rows, 1};
     rc = encode(&p.tmA[0], act_dtype, 4, a.in.ptr, dims, str, box, ck);
     for (int v = 1; v < 4 && !rc; ++v) p.tmA[v] = p.tmA[0];
   } else {
@@ -331,7 +452,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
       cuuint64_t dims[4] = {dim0, (cuuint64_t)a.in.W / 2, (cuuint64_t)a.in.H / 2, (cuuint64_t)a.batch};
       cuuint64_t str[3] = {(cuuint64_t)2 * a.in.pix_stride * esz, (cuuint64_t)2 * a.in.W * a.in.pix_stride * esz,
                            (cuuint64_t)a.in.H * a.in.W * a.in.pix_stride * esz};
-      cuuint32_t box[4] = {(cuuint32_t)ck, TILE_X, TILE_Y, 1};
+      cuuint32_t box[4] = {(cuuint32_t)ck, TILE_X, box_rows, 1};
       rc = encode(&p.tmA[v], act_dtype, 4, ptr, dims, str, box, ck);
     }
   }
@@ -346,32 +467,53 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
   p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
-  p.tiles_x = a.out.W / TILE_X; p.Ho = a.out.H; p.Wo = a.out.W; p.out_stride = a.out.pix_stride;
+  p.tiles_x = a.out.W / TILE_X; p.tiles_per_img = p.tiles_x * (a.out.H / TILE_Y);
+  p.total_tiles = p.tiles_per_img * a.batch;
+  p.Ho = a.out.H; p.Wo = a.out.W; p.out_stride = a.out.pix_stride;
   p.res_stride = a.has_res ? a.res.pix_stride : 0;
-  p.tmem_cols = 32;
-  while (p.tmem_cols < a.cout_pad) p.tmem_cols *= 2;
+  // per super-tile two accumulators (left/right half) of acc_stride columns (power of two >= cout_pad);
+  // double buffered when 4 of them fit the 512 TMEM columns
+  p.acc_stride = 16;
+  while (p.acc_stride < a.cout_pad) p.acc_stride *= 2;
+  p.nbuf = (4 * p.acc_stride <= 512) ? 2 : 1;
+  p.tmem_cols = p.nbuf * 2 * p.acc_stride < 32 ? 32 : p.nbuf * 2 * p.acc_stride;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N, M=128
   const uint32_t fmt = act_dtype == ACR_DT_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.cout_pad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-  const size_t stage = (((size_t)TILE_M * ck * 2 + (size_t)a.cout_pad * ck * 2) + 1023) & ~(size_t)1023;
-  const int kiters = p.taps * p.cchunks;
-  int S = kiters < 4 ? kiters : 4;
-  while (S > 1 && S * stage + 2048 > 200 * 1024) --S;
-  p.num_stages = S;
-  pl->smem = S * stage + 1024 /*alignment slack*/ + 8 * (2 * S + 2) + 64;
-  pl->tiles = p.tiles_x * (a.out.H / TILE_Y);
+  // shared-memory plan
+  p.a_stage_bytes = (uint32_t)(box_rows * TILE_X) * ck * 2;
+  p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
+  const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
+  const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/;
+  const int nA = p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks;
+  p.b_resident = (b_total + 3 * (size_t)p.a_stage_bytes + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
+  if (p.b_resident) {
+    p.b_region_bytes = (uint32_t)((b_total + 1023) & ~(size_t)1023);
+    p.SB = 0;
+  } else {
+    p.SB = 4;
+    while (p.SB > 2 && (size_t)p.SB * p.b_block_bytes + 3 * (size_t)p.a_stage_bytes + fixed > (size_t)SMEM_BUDGET) --p.SB;
+    p.b_region_bytes = (uint32_t)(((size_t)p.SB * p.b_block_bytes + 1023) & ~(size_t)1023);
+  }
+  int SA = (int)(((size_t)SMEM_BUDGET - fixed - p.b_region_bytes) / p.a_stage_bytes);
+  if (SA > 8) SA = 8;
+  if (SA > 2 * nA) SA = 2 * nA;  // no point in more stages than two super-tiles' worth of loads
+  if (SA < 2) { set_error("conv_tc: shared memory plan does not fit (cout_pad %d, ck %d)", a.cout_pad, ck); delete pl; return ACR_B200_EINVAL; }
+  p.SA = SA;
+  pl->smem = fixed + p.b_region_bytes + (size_t)SA * p.a_stage_bytes;
+  pl->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   *out = pl;
   return ACR_B200_OK;
 }
 
 template <int CK, typename T>
 static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
-  static size_t configured = 0;
-  if (pl->smem > configured) {
-    ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    configured = 220 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    configured = true;
   }
-  conv_tc_kernel<CK, T><<<dim3(pl->tiles, pl->batch), TC_THREADS, pl->smem, st>>>(pl->p);
+  conv_tc_kernel<CK, T><<<pl->grid, TC_THREADS, pl->smem, st>>>(pl->p);
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
