@@ -62,6 +62,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (the pattern CUTLASS uses so that tcgen05/TMA issue stays on the uniform
+// datapath without per-lane emulation loops)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -100,6 +107,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, with the 64-bit descriptors passed as (lo, hi) register pairs: the issuing thread only adds
+// small constants to the 32-bit `lo` words between MMAs (the issue loop is a single thread, so every
+// integer instruction in it is on the tensor pipe's critical path)
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -202,13 +222,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      if (P.b_resident) {  // whole weight tensor once per CTA
+    // (whole warp stays converged; one elected lane issues)
+    {
+      if (P.b_resident && elect_one_sync()) {  // whole weight tensor once per CTA
         const int nblk = P.taps * P.cchunks;
         mbar_expect_tx(bres_bar, (uint32_t)nblk * P.b_block_bytes);
         for (int i = 0; i < nblk; ++i)
           tma_load_2d(b_base + (uint32_t)i * P.b_block_bytes, &P.tmB, bres_bar, (i / P.cchunks) * P.cin_pad + (i % P.cchunks) * CK, 0);
       }
+      __syncwarp();
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -232,15 +254,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
           mbar_wait(emptyA(sa), pha ^ 1u);
-          mbar_expect_tx(fullA(sa), P.a_stage_bytes);
-          tma_load_4d(a_base + (uint32_t)sa * P.a_stage_bytes, &P.tmA[view], fullA(sa), cc * CK, x0 + dx, y0 + dy, n);
+          if (elect_one_sync()) {
+            mbar_expect_tx(fullA(sa), P.a_stage_bytes);
+            tma_load_4d(a_base + (uint32_t)sa * P.a_stage_bytes, &P.tmA[view], fullA(sa), cc * CK, x0 + dx, y0 + dy, n);
+          }
+          __syncwarp();
           if (++sa == SA) { sa = 0; pha ^= 1u; }
           if (!P.b_resident) {
             for (int sub = 0; sub < nsub; ++sub) {
               const int tap = P.patch_mode ? sub * 3 + tap0 : tap0;
               mbar_wait(emptyB(sb), phb ^ 1u);
-              mbar_expect_tx(fullB(sb), P.b_block_bytes);
-              tma_load_2d(b_base + (uint32_t)sb * P.b_block_bytes, &P.tmB, fullB(sb), tap * P.cin_pad + cc * CK, 0);
+              if (elect_one_sync()) {
+                mbar_expect_tx(fullB(sb), P.b_block_bytes);
+                tma_load_2d(b_base + (uint32_t)sb * P.b_block_bytes, &P.tmB, fullB(sb), tap * P.cin_pad + cc * CK, 0);
+              }
+              __syncwarp();
               if (++sb == SB) { sb = 0; phb ^= 1u; }
             }
           }
@@ -249,8 +277,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
+    // (whole warp stays converged; one elected lane issues the tcgen05 instructions)
+    {
       if (P.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+      // descriptor words that never change (see make_smem_desc): hi = SBO | version | layout, lo = addr>>4 | LBO
+      const uint32_t hi_a = (Cfg::kSBO_A >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+      const uint32_t hi_b = (Cfg::kAtom >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+      const uint32_t lo_flags = 1u << 16;
+      const uint32_t idesc = P.idesc, acc_stride = (uint32_t)P.acc_stride;
+      const uint32_t b_block16 = P.b_block_bytes >> 4, a_stage16 = P.a_stage_bytes >> 4;
+      const uint32_t a_lo_base = ((a_base >> 4) & 0x3FFF) | lo_flags, b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
+      const bool resident = P.b_resident != 0, patch = P.patch_mode != 0;
+      const int cchunks = P.cchunks;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
@@ -259,35 +297,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;   // how often this buffer was used before
         mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator pair
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 2 * P.acc_stride);
+        const uint32_t d0 = tmem_base + (uint32_t)buf * 2u * acc_stride, d1 = d0 + acc_stride;
         uint32_t accum = 0;
+        int cc = 0, t0 = 0;   // patch: (cc, kx) ; tap mode: (tap, cc)
         for (int a = 0; a < nA; ++a) {
-          int cc, tap0;
-          if (P.patch_mode) { cc = a / 3; tap0 = a % 3; } else { tap0 = a / P.cchunks; cc = a % P.cchunks; }
           mbar_wait(fullA(sa), pha);
           tc_fence_after();
-          const uint32_t a_src = a_base + (uint32_t)sa * P.a_stage_bytes;
+          const uint32_t a_lo = a_lo_base + (uint32_t)sa * a_stage16;
+          const int tap_first = patch ? t0 : t0;   // tap of sub 0 (patch: ky=0 -> tap = kx)
+#pragma unroll 1
           for (int sub = 0; sub < nsub; ++sub) {
-            const int tap = P.patch_mode ? sub * 3 + tap0 : tap0;
-            uint32_t b_src;
-            if (P.b_resident) b_src = b_base + (uint32_t)(tap * P.cchunks + cc) * P.b_block_bytes;
-            else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_src = b_base + (uint32_t)sb * P.b_block_bytes; }
-            const uint32_t a_tap = a_src + (uint32_t)sub * Cfg::kSBO_A;  // ky shift = one 16-pixel box row
+            const int tap = patch ? sub * 3 + tap_first : tap_first;
+            uint32_t b_lo;
+            if (resident) b_lo = b_lo_base + (uint32_t)(tap * cchunks + cc) * b_block16;
+            else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
+            const uint32_t a_tap = a_lo + (uint32_t)sub * (Cfg::kSBO_A >> 4);  // ky shift = one 16-pixel box row
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                                // left / right 8 output columns
-#pragma unroll
-              for (int ks = 0; ks < CK / 16; ++ks)
-                umma_f16(d_tmem + (uint32_t)(h * P.acc_stride),
-                         make_smem_desc(a_tap + h * Cfg::kAtom + ks * 32, Cfg::kSBO_A, Cfg::kLayout),
-                         make_smem_desc(b_src + ks * 32, Cfg::kAtom, Cfg::kLayout), P.idesc, (accum | (uint32_t)ks) ? 1u : 0u);
+              for (int ks = 0; ks < CK / 16; ++ks) {
+                const uint32_t acc_flag = (ks == 0) ? accum : 1u;
+                umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);                        // left 8 columns
+                umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);  // right 8 columns
+              }
+              if (!resident) umma_commit(emptyB(sb));
+              if (sub == nsub - 1) umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
             }
+            __syncwarp();
             accum = 1u;  // only the very first k-step of each accumulator overwrites
-            if (!P.b_resident) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
+            if (!resident) { if (++sb == SB) { sb = 0; phb ^= 1u; } }
           }
-          umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
           if (++sa == SA) { sa = 0; pha ^= 1u; }
+          if (patch) { if (++t0 == 3) { t0 = 0; ++cc; } } else { if (++cc == cchunks) { cc = 0; ++t0; } }
         }
-        umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
+        if (elect_one_sync()) umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
+        __syncwarp();
       }
     }
   } else {

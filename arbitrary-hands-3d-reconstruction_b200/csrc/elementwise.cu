@@ -16,26 +16,29 @@ namespace acr {
 
 // ------------------------------------------------------------------------------------ stem
 // HigherResolutionNet.forward :832-835: x/255*2-1, conv1 3x3 s2 (3->64) + bn1 + relu.
-// weights: fp32 [27][64] (tap-major, BN folded), bias fp32 [64].  thread = (pixel, 16 channels)
+// weights: fp32 [27][64] (tap-major, BN folded), bias fp32 [64].  thread = one output pixel x all 64
+// channels: the 27 normalised inputs are scalars, the 64 weights of a tap are broadcast float4 reads
+// from shared memory, 64 fp32 accumulators live in registers (1728 FMA per 4 B of input).
 template <typename T>
-__global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ img, T* __restrict__ out,
+__global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ img, T* __restrict__ out,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    int H, int W, int out_stride, long long total) {
-  __shared__ float s_w[27 * 64];
-  __shared__ float s_b[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += 256) s_w[i] = w[i];
+  __shared__ __align__(16) float s_w[27 * 64];
+  __shared__ __align__(16) float s_b[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += 128) s_w[i] = w[i];
   if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid & 3);
-  const long long pix = gid >> 2;
+  const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= total) return;
   const int Ho = H / 2, Wo = W / 2;
   const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
   const long long b = pix / ((long long)Wo * Ho);
-  float acc[16];
+  float acc[64];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = s_b[cg * 16 + c];
+  for (int c = 0; c < 64; c += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(&s_b[c]);
+    acc[c] = b4.x; acc[c + 1] = b4.y; acc[c + 2] = b4.z; acc[c + 3] = b4.w;
+  }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy * 2 + ky - 1;
@@ -48,25 +51,29 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ i
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float xn = (float)px[ci] / 255.f * 2.0f - 1.0f;
-        const float* wr = &s_w[((ky * 3 + kx) * 3 + ci) * 64 + cg * 16];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[((ky * 3 + kx) * 3 + ci) * 64]);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = fmaf(xn, wr[c], acc[c]);
+        for (int c = 0; c < 16; ++c) {
+          const float4 w4 = wr[c];
+          acc[4 * c + 0] = fmaf(xn, w4.x, acc[4 * c + 0]); acc[4 * c + 1] = fmaf(xn, w4.y, acc[4 * c + 1]);
+          acc[4 * c + 2] = fmaf(xn, w4.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(xn, w4.w, acc[4 * c + 3]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
-  T* o = out + pix * out_stride + cg * 16;
-  *reinterpret_cast<uint4*>(o) = pack8<T>(acc);
-  *reinterpret_cast<uint4*>(o + 8) = pack8<T>(acc + 8);
+  for (int c = 0; c < 64; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  T* o = out + pix * out_stride;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(o + c * 8) = pack8<T>(acc + c * 8);
 }
 
 int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, const float* bias, int batch,
                 int act_dtype, cudaStream_t st) {
   ACR_CHECK_ARG(out.C == 64 && out.H * 2 == img.H && out.W * 2 == img.W && img.dtype == ACR_DT_U8,
                 "stem: shape mismatch");
-  const long long total = (long long)batch * out.H * out.W * 4;
-  ACR_DISPATCH_ACT(act_dtype, stem_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  const long long total = (long long)batch * out.H * out.W;
+  ACR_DISPATCH_ACT(act_dtype, stem_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
                                   (const uint8_t*)img.ptr, (T*)out.ptr, w, bias, img.H, img.W, out.pix_stride, total));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
@@ -293,14 +300,20 @@ __global__ void __launch_bounds__(256) pool_kernel(TensorRef feat, TensorRef log
       ssum += w;
     }
     __syncthreads();
-    for (int pp = 0; pp < 32; ++pp) {
-      const float f = to_f32<T>(ft[(size_t)(q + pp) * feat.pix_stride + t]);
-      const float4* wr = reinterpret_cast<const float4*>(&s_w[pp][0]);
+    for (int p8 = 0; p8 < 32; p8 += 8) {
+      T fv[8];   // 8 independent loads in flight before the FMA block
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 w4 = wr[i];
-        acc[i * 4 + 0] = fmaf(w4.x, f, acc[i * 4 + 0]); acc[i * 4 + 1] = fmaf(w4.y, f, acc[i * 4 + 1]);
-        acc[i * 4 + 2] = fmaf(w4.z, f, acc[i * 4 + 2]); acc[i * 4 + 3] = fmaf(w4.w, f, acc[i * 4 + 3]);
+      for (int u = 0; u < 8; ++u) fv[u] = ft[(size_t)(q + p8 + u) * feat.pix_stride + t];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float f = to_f32<T>(fv[u]);
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[p8 + u][0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w4 = wr[i];
+          acc[i * 4 + 0] = fmaf(w4.x, f, acc[i * 4 + 0]); acc[i * 4 + 1] = fmaf(w4.y, f, acc[i * 4 + 1]);
+          acc[i * 4 + 2] = fmaf(w4.z, f, acc[i * 4 + 2]); acc[i * 4 + 3] = fmaf(w4.w, f, acc[i * 4 + 3]);
+        }
       }
     }
   }

@@ -173,14 +173,16 @@ def run_b200(args):
     frames_host = torch.randint(0, 256, (B, 512, 512, 3), generator=gi, dtype=torch.uint8).pin_memory()
     frames_dev = frames_host.to(dev)
     offsets = torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]], device=dev).repeat(B, 1)
+    from acr_b200.dist import gather_vertices
     gather_buf = torch.empty(world, 2 * B, 778, 3, device=dev) if world > 1 else None
+    gather_cnt = torch.empty(world, 8, dtype=torch.int32, device=dev) if world > 1 else None
     verts_host = torch.empty(2 * B, 778, 3).pin_memory()
     counts_host = torch.empty(8, dtype=torch.int32).pin_memory()
 
     def step(frames):
         bufs, mano = app.fused_forward(frames, offsets)
         if world > 1:   # the one collective of the path: vertices of every shard on every rank (NVLink)
-            dist.all_gather_into_tensor(gather_buf.view(-1), mano["verts"].view(-1))
+            gather_vertices(mano["verts"], bufs.counts, gather_buf, gather_cnt)
         return bufs, mano
 
     def sync_all():
