@@ -125,6 +125,15 @@ class Engine:
                 "pack_conv " + wkey)
         return blob.add(wp), blob.add(bias)
 
+    def _pack_raw(self, blob: _Blob, w: np.ndarray, cin_pad: int, cout_pad: int) -> int:
+        cout, cin, k, _ = w.shape
+        wp = np.zeros((cout_pad, k * k, cin_pad), np.uint16)
+        bias = np.zeros(cout_pad, np.float32)
+        w = np.ascontiguousarray(w, np.float32)
+        L.check(self.lib.acr_b200_pack_conv(w.ctypes.data, None, None, None, None, None, BN_EPS, cout, cin, k,
+                                            cout_pad, cin_pad, self.dt, wp.ctypes.data, bias.ctypes.data), "pack_conv")
+        return blob.add(wp)
+
     # --------------------------------------------------------------------- plan
     def _build(self, sd, reuse_memory: bool) -> None:
         spec, B = self.spec, self.batch
@@ -166,8 +175,10 @@ class Engine:
                 if op.attrs["side"] == "l":   # one launch serves both sides
                     recs.append(dict(kind=L.OP_PARTHEAD, out=pooled, ins=[part],
                                      aux=[bias_img["l"], bias_img["r"], pare["l"], pare["r"]]))
-                s = op.attrs["side"]
-                recs.append(dict(kind=L.OP_FINALCONV, out=op.out, ins=[op.ins[1], op.ins[2], bias_img[s]], side=s))
+                s = op.attrs["side"]   # folded contact_layers[4|5]: 1x1 conv 128 -> 109 with a per-image bias
+                recs.append(dict(kind=L.OP_CONV_REF if self.debug_ref_conv else L.OP_CONV, out=op.out,
+                                 ins=[op.ins[1]], aux=[bias_img[s]],
+                                 attrs=dict(k=1, s=1, relu=False, residual=False, pow11=False, fold_side=s)))
             elif op.kind == "coordcat":
                 recs.append(dict(kind=L.OP_COORD, out=op.out, ins=[op.ins[0]]))
             else:
@@ -235,8 +246,25 @@ class Engine:
             if r["kind"] in (L.OP_CONV, L.OP_CONV_REF):
                 x = r["ins"][0]
                 o.k, o.stride, o.relu, o.has_residual = a["k"], a["s"], int(a["relu"]), int(a["residual"])
-                o.cin_pad, o.cout_pad = _rup(x.C, 16), _rup(r["out"].C, 16)
-                o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
+                # K per tap: 33/34-channel inputs are padded to ONE 64-channel chunk (TMA zero-fills the
+                # channels beyond the 48-wide buffer) instead of three 16-channel chunks: a TMA box costs
+                # ~620 clk whatever its size, so fewer, fatter boxes win (tools/tma_bench.cu)
+                o.cin_pad = 64 if 32 < x.C <= 64 else _rup(x.C, 16)
+                o.cout_pad = _rup(r["out"].C, 16)
+                if "fold_side" in a:
+                    # out = W[:, :109].pm + W[:, 109:112].pm[:3] + (b + W[:, 112:].pare),  pm = [cam3 | params106]
+                    # (acr/model.py:158-164); input channel order of the 128-wide tensor: params at 0..105, cam at 112..114
+                    W = f32(f"contact_layers.{4 if a['fold_side'] == 'l' else 5}.weight").reshape(109, 218)
+                    weff = np.zeros((109, 128, 1, 1), np.float32)
+                    weff[:, :106, 0, 0] = W[:, 3:109]
+                    weff[:, 112:115, 0, 0] = W[:, 0:3] + W[:, 109:112]
+                    o.cin_pad = 128
+                    o.w_offset[0] = self._pack_raw(blob, weff, o.cin_pad, o.cout_pad)
+                    o.shift[0] = 1      # ACR_CONV_BIAS_PER_IMAGE (aux[0] = bias_img from the part head)
+                else:
+                    o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
+                    if a.get("pow11"):
+                        o.shift[0] = 2  # ACR_CONV_POW11_CH0
             elif r["kind"] == L.OP_STEM:
                 w = f32(a["w"] + ".weight")                                   # (64,3,3,3) OIHW
                 g_, b_, m_, v_ = (f32(f"{a['bn']}.{n}") for n in ("weight", "bias", "running_mean", "running_var"))
@@ -255,13 +283,6 @@ class Engine:
                         "contact_layers.5.weight", "contact_layers.4.bias", "contact_layers.5.bias"]
                 for j, k in enumerate(keys):
                     o.w_offset[j] = blob.add(f32(k).reshape(-1))
-            elif r["kind"] == L.OP_FINALCONV:
-                W = f32(f"contact_layers.{4 if r['side'] == 'l' else 5}.weight").reshape(109, 218)
-                weff = W[:, :109].copy()
-                weff[:, :3] += W[:, 109:112]
-                wt = np.zeros((112, 112), np.float32)                         # [in][out]
-                wt[:109, :109] = weff.T
-                o.w_offset[0] = blob.add(wt)
         self.n_ops = len(recs)
         self._cops = cops
         self.weights = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).to(self.device)

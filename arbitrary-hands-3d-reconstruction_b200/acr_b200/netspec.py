@@ -74,7 +74,7 @@ class NetSpec:
     def conv(self, x: Tensor, wkey: str, bnkey: Optional[str], cout: int, k: int,
              s: int = 1, relu: bool = False, bias: bool = False,
              residual: Optional[Tensor] = None, out_dtype: str = "act",
-             out: Optional[Tensor] = None, hint: str = "") -> Tensor:
+             out: Optional[Tensor] = None, hint: str = "", pow11: bool = False) -> Tensor:
         self._reg(wkey + ".weight", (cout, x.C, k, k), "conv_w")
         if bias:
             self._reg(wkey + ".bias", (cout,), "conv_b")
@@ -84,7 +84,7 @@ class NetSpec:
         y = out if out is not None else self._t(cout, Ho, Wo, hint or wkey.split(".")[-1], out_dtype)
         self.ops.append(Op("conv", y, [x] + ([residual] if residual is not None else []),
                            dict(w=wkey, bn=bnkey, bias=bias, k=k, s=s, relu=relu,
-                                residual=residual is not None)))
+                                residual=residual is not None, pow11=pow11)))
         return y
 
     def fuse(self, terms: List[Tuple[Tensor, int]], relu=True, out: Optional[Tensor] = None) -> Tensor:
@@ -206,14 +206,25 @@ def build_acr_spec(input_size: int = 512) -> NetSpec:
 
     # ---- global heads (acr/model.py:68-101, 288-313): 8 stacks on the 34-ch map
     heads = {}
+    raw128 = {}
     for side in ("l", "r"):
+        # params (106) and cam (3, scale channel through 1.1**x) heads write 16-bit slices [0,112) and
+        # [112,128) of one 128-channel tensor: the input of the folded contact_layers[4|5] conv
+        raw128[side] = g._t(128, F // 2, F // 2, f"{side}_raw128")
+        slices = {"params": Tensor(f"{side}_params_raw", 106, F // 2, F // 2, "act", base=raw128[side], c_off=0),
+                  "cam": Tensor(f"{side}_cam_raw", 3, F // 2, F // 2, "act", base=raw128[side], c_off=112)}
+        for t in slices.values():
+            g.tensors[t.name] = t
         for idx, (nm, co) in {1: ("params", 106), 2: ("center", 1), 3: ("cam", 3), 4: ("prior", 106)}.items():
             p = f"{side}_final_layers.{idx}"
             h = g.conv(xcat, p + ".0.0", p + ".0.1", 64, 3, s=2, relu=True, bias=True)
             for blk in range(2):
                 h = _basic_block(g, h, f"{p}.1.{blk}.0", 64)
-            heads[(side, nm)] = g.conv(h, p + ".2", None, co, 1, bias=True, out_dtype="f32",
-                                       hint=f"{side}_{nm}")
+            if nm in slices:
+                heads[(side, nm)] = g.conv(h, p + ".2", None, co, 1, bias=True, out=slices[nm], pow11=(nm == "cam"))
+            else:
+                heads[(side, nm)] = g.conv(h, p + ".2", None, co, 1, bias=True, out_dtype="f32",
+                                           hint=f"{side}_{nm}")
     for k, t in heads.items():
         g.tensors[f"{k[0]}_{k[1]}_raw"] = t
 
@@ -236,8 +247,7 @@ def build_acr_spec(input_size: int = 512) -> NetSpec:
     g.tensors["pooled"] = pooled
     for side in ("l", "r"):
         t = g._t(109, F // 2, F // 2, f"{side}_params_maps", "f32")
-        g.ops.append(Op("parthead", t, [pooled, heads[(side, "cam")], heads[(side, "params")]],
-                        dict(side=side)))
+        g.ops.append(Op("parthead", t, [pooled, raw128[side]], dict(side=side)))
         g.tensors[f"{side}_params_maps"] = t
         g.tensors[f"{side}_center_map"] = heads[(side, "center")]
         g.tensors[f"{side}_prior_maps"] = heads[(side, "prior")]

@@ -160,7 +160,7 @@ struct ConvTcParams {
   const float* bias;
   const void* res;
   void* out;
-  int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32;
+  int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
   int patch_mode, b_resident, SA, SB;
   uint32_t a_stage_bytes, b_block_bytes, b_region_bytes;
   int tmem_cols, acc_stride, nbuf;
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
   }
-  for (int i = threadIdx.x; i < P.npad; i += TC_THREADS) s_bias[i] = P.bias[i];
+  if (!P.bias_per_image)
+    for (int i = threadIdx.x; i < P.npad; i += TC_THREADS) s_bias[i] = P.bias[i];
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -346,6 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int oy = (rem / P.tiles_x) * TILE_Y + (r >> 3), ox = (rem % P.tiles_x) * TILE_X + h * HALF_X + (r & 7);
       const size_t pix = ((size_t)n * P.Ho + oy) * P.Wo + ox;
       const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride : nullptr;
+      // bias: per CTA from shared memory, or (folded part-head conv) one row per image from global
+      const float* bsrc = P.bias_per_image ? P.bias + (size_t)n * P.npad : s_bias;
       uint4 rr[4][2];
       if (resp) {   // prefetch the first 64 residual channels while the MMAs are still running
 #pragma unroll
@@ -385,10 +388,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           float f[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);
+            const float4 b4 = *reinterpret_cast<const float4*>(bsrc + c0 + 4 * i);
             f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
             f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
           }
+          if (P.pow11_ch0 && c0 == 0) f[0] = powf(1.1f, f[0]);   // cam scale channel (acr/model.py:95-96)
           if (resp) {
             float x[16];
             unpack8<T>(rr[c][0], x);
@@ -510,6 +514,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
   p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
+  p.bias_per_image = a.bias_per_image; p.pow11_ch0 = a.pow11_ch0;
   p.tiles_x = a.out.W / TILE_X; p.tiles_per_img = p.tiles_x * (a.out.H / TILE_Y);
   p.total_tiles = p.tiles_per_img * a.batch;
   p.Ho = a.out.H; p.Wo = a.out.W; p.out_stride = a.out.pix_stride;

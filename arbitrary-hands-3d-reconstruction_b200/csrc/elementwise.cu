@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128) conv_ref_kernel(ConvArgs a, long long tot
       }
     }
   }
+  if (a.pow11_ch0 && cg == 0) acc[0] = powf(1.1f, acc[0]);
   if (a.has_res) {
     const T* rp = (const T*)a.res.ptr + ((size_t)b * a.res.H * a.res.W + (size_t)oy * Wo + ox) * a.res.pix_stride + cg * 8;
     float r[8];
@@ -424,58 +425,6 @@ __global__ void __launch_bounds__(256) parthead_kernel(PartHeadArgs a) {
 
 int launch_parthead(const PartHeadArgs& a, cudaStream_t st) {
   parthead_kernel<<<a.batch, 256, 0, st>>>(a);
-  ACR_CHECK_LAUNCH();
-  return ACR_B200_OK;
-}
-
-// ------------------------------------------------------------------------- folded final conv
-// contact_layers[4|5] (:163-164) with the concat (:158-161) folded:
-//   out = W[:, :109] . pm + W[:, 109:112] . pm[:3] + (b + W[:, 112:] . pare)       pm = [1.1**cam0, cam1, cam2, params]
-// w_eff_t is (112 in, 112 out) fp32, zero padded.  CTA = 32 pixels, thread = output channel.
-__global__ void __launch_bounds__(128) final_conv_kernel(FinalConvArgs a) {
-  __shared__ __align__(16) float s_in[112][32];
-  const int t = threadIdx.x;
-  const size_t pix0 = (size_t)blockIdx.x * 32;               // global pixel index over (b, y, x)
-  const int npix = a.out.H * a.out.W;
-  const int b = (int)(pix0 / npix);
-  const float* cam = (const float*)a.cam.ptr;
-  const float* prm = (const float*)a.prm.ptr;
-  for (int e = t; e < 32 * 112; e += 128) {
-    const int px = e / 112, i = e % 112;
-    float v = 0.f;
-    if (i < 3) {
-      v = cam[(pix0 + px) * a.cam.pix_stride + i];
-      if (i == 0) v = powf(1.1f, v);
-    } else if (i < 109) {
-      v = prm[(pix0 + px) * a.prm.pix_stride + (i - 3)];
-    }
-    s_in[i][px] = v;
-  }
-  __syncthreads();
-  if (t >= 112) return;
-  float acc[32];
-  const float bias = a.bias_img[(size_t)b * 112 + t];
-#pragma unroll
-  for (int p = 0; p < 32; ++p) acc[p] = bias;
-  for (int i = 0; i < 109; ++i) {
-    const float w = __ldg(a.w_eff + (size_t)i * 112 + t);
-    const float4* r = reinterpret_cast<const float4*>(&s_in[i][0]);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 x = r[q];
-      acc[q * 4 + 0] = fmaf(w, x.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(w, x.y, acc[q * 4 + 1]);
-      acc[q * 4 + 2] = fmaf(w, x.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(w, x.w, acc[q * 4 + 3]);
-    }
-  }
-  float* o = (float*)a.out.ptr;
-#pragma unroll
-  for (int p = 0; p < 32; ++p) o[(pix0 + p) * a.out.pix_stride + t] = acc[p];
-}
-
-int launch_final_conv(const FinalConvArgs& a, cudaStream_t st) {
-  const long long total = (long long)a.batch * a.out.H * a.out.W;
-  ACR_CHECK_ARG(total % 32 == 0 && (a.out.H * a.out.W) % 32 == 0 && a.out.pix_stride >= 112, "final_conv: shapes");
-  final_conv_kernel<<<(unsigned)(total / 32), 128, 0, st>>>(a);
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }

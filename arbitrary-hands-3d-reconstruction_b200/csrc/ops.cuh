@@ -14,7 +14,7 @@ struct ConvArgs {
   TensorRef in, out, res;
   const void* w;           // [cout_pad][k*k][cin_pad] 16-bit
   const float* bias;       // [cout_pad] (or [B][cout_pad] when bias_per_image)
-  int k, stride, relu, has_res, cin_pad, cout_pad, bias_per_image, batch;
+  int k, stride, relu, has_res, cin_pad, cout_pad, bias_per_image, pow11_ch0, batch;
 };
 
 struct FuseArgs {
@@ -49,14 +49,6 @@ struct PartHeadArgs {
   int batch;
 };
 int launch_parthead(const PartHeadArgs& a, cudaStream_t st);
-struct FinalConvArgs {         // folded contact_layers[4|5]: 109 -> 109 1x1 conv + per-image bias
-  TensorRef cam, prm, out;     // fp32 maps: cam (.,16), params (.,112), out (.,112)
-  const float* w_eff;          // (112,112) fp32, rows = out channel, cols = in channel [cam3|params106|pad]
-  const float* bias_img;       // (B,112)
-  int batch;
-};
-int launch_final_conv(const FinalConvArgs& a, cudaStream_t st);
-
 // tcgen05 implicit-GEMM conv (conv_tc.cu)
 struct ConvTcPlan;   // holds the TMA tensor maps of one conv op
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out);

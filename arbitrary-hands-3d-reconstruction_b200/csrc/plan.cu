@@ -33,7 +33,13 @@ static int make_conv_args(const acr_b200_op& op, int batch, char* arena, const c
   a->w = weights + op.w_offset[0];
   a->bias = reinterpret_cast<const float*>(weights + op.w_offset[1]);
   a->k = op.k; a->stride = op.stride; a->relu = op.relu;
-  a->cin_pad = op.cin_pad; a->cout_pad = op.cout_pad; a->bias_per_image = 0; a->batch = batch;
+  a->cin_pad = op.cin_pad; a->cout_pad = op.cout_pad; a->batch = batch;
+  a->bias_per_image = (op.shift[0] & ACR_CONV_BIAS_PER_IMAGE) ? 1 : 0;
+  a->pow11_ch0 = (op.shift[0] & ACR_CONV_POW11_CH0) ? 1 : 0;
+  if (a->bias_per_image) {
+    ACR_CHECK_ARG(op.aux[0].dtype == ACR_DT_F32 && op.aux[0].pix_stride >= op.cout_pad, "conv: per-image bias tensor (aux[0]) malformed");
+    a->bias = reinterpret_cast<const float*>(arena + op.aux[0].offset);
+  }
   ACR_CHECK_ARG((op.k == 1 || op.k == 3) && (op.stride == 1 || op.stride == 2), "conv: k/stride unsupported");
   ACR_CHECK_ARG(a->out.H * op.stride == a->in.H && a->out.W * op.stride == a->in.W, "conv: spatial mismatch");
   ACR_CHECK_ARG(op.cout_pad % 16 == 0 && op.cin_pad % 16 == 0 && op.cout_pad <= 256, "conv: padded channel counts");
@@ -97,18 +103,6 @@ static int run_one(const acr_b200_op& op, int batch, char* arena, const char* we
       a.pare[1] = reinterpret_cast<float*>(arena + op.aux[3].offset);
       a.batch = batch;
       return launch_parthead(a, st);
-    }
-    case ACR_OP_FINALCONV: {
-      FinalConvArgs a;
-      a.cam = resolve(op.in[0], arena, external);
-      a.prm = resolve(op.in[1], arena, external);
-      a.out = resolve(op.out, arena, external);
-      a.bias_img = reinterpret_cast<const float*>(arena + op.in[2].offset);
-      a.w_eff = reinterpret_cast<const float*>(weights + op.w_offset[0]);
-      a.batch = batch;
-      ACR_CHECK_ARG(a.cam.dtype == ACR_DT_F32 && a.prm.dtype == ACR_DT_F32 && a.out.dtype == ACR_DT_F32,
-                    "final_conv: fp32 maps expected");
-      return launch_final_conv(a, st);
     }
     default:
       set_error("unknown op kind %d", op.kind);

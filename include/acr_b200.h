@@ -125,6 +125,7 @@ enum {
   ACR_OP_CONV_REF = 8,    /* debug: same contract as ACR_OP_CONV on CUDA cores (tests only)     */
   ACR_OP_FINALCONV = 9    /* folded contact_layers[4|5]: 109->109 1x1 conv + per-image bias     */
 };
+enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2 };
 enum { ACR_DT_BF16 = 0, ACR_DT_F16 = 1, ACR_DT_F32 = 2, ACR_DT_U8 = 3 };
 
 typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image extents)  */
@@ -138,15 +139,17 @@ typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image
 /* One launch.  Which fields are read depends on `kind`:
  *  STEM      in[0]=image(u8,external) out; w_offset[0]=fp32 [27][64] folded weights, [1]=fp32 bias[64]
  *  CONV(_REF) in[0]=x, in[1]=residual (has_residual) out; w_offset[0]=packed 16-bit weights
- *            [cout_pad][k*k][cin_pad], w_offset[1]=fp32 bias[cout_pad]
+ *            [cout_pad][k*k][cin_pad], w_offset[1]=fp32 bias[cout_pad]; shift[0] = flag bits:
+ *            ACR_CONV_BIAS_PER_IMAGE (bias = fp32 (B,cout_pad) tensor aux[0] in the arena instead of
+ *            w_offset[1]) | ACR_CONV_POW11_CH0 (output channel 0 -> 1.1**x, acr/model.py:95-96)
  *  FUSE      in[0..n_in) with shift[i]; out
  *  BILINEAR2X / COORD (fparam unused; COORD writes channels [in[0].C, pix_stride) of `out`)
  *  POOL      in[0]=contact features (256ch), in[1]=segm logits; out = partials (fp32, 1x1xC)
  *  PARTHEAD  in[0]=partials; out=pooled (fp32 256*32); aux[0..1]=bias_img l,r (112); aux[2..3]=
  *            pare l,r (106); w_offset[0..1]=LC weights l,r; [2],[3]=shape conv w,b; [4..5]=Linear w
  *            l,r; [6..7]=Linear b; [8..9]=final conv w (109,218) l,r; [10..11]=final conv b
- *  FINALCONV in[0]=cam map, in[1]=params map (fp32), in[2]=bias_img; out (fp32 112);
- *            w_offset[0]=fp32 (112 in,112 out) folded weights                              */
+ *  FINALCONV (retired: the folded contact_layers[4|5] conv now runs as a CONV with
+ *            ACR_CONV_BIAS_PER_IMAGE on the tensor cores)                                  */
 typedef struct acr_b200_op {
   int32_t kind;
   int32_t n_in;

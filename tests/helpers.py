@@ -55,13 +55,13 @@ def u16_to_float(a: np.ndarray, dt) -> torch.Tensor:
 
 
 def run_conv_case(kind, B, H, W, cin, cout, k, s, relu, residual, bias, bn, out_f32, dt=L.DT_BF16, seed=0,
-                  in_stride=None):
+                  in_stride=None, cin_pad=None):
     """Runs one conv through acr_b200_run_op on the GPU and returns (got, expected) fp32 NCHW."""
     import torch.nn.functional as Fn
     g = torch.Generator().manual_seed(seed)
     tdt = torch.bfloat16 if dt == L.DT_BF16 else torch.float16
-    cin_pad, cout_pad = rup(cin, 16), rup(cout, 16)
-    in_stride = in_stride or cin_pad
+    in_stride = in_stride or rup(cin, 16)
+    cin_pad, cout_pad = cin_pad or rup(cin, 16), rup(cout, 16)
     Ho, Wo = H // s, W // s
     x = torch.randn(B, cin, H, W, generator=g)
     w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5

@@ -60,6 +60,16 @@ def test_conv_tc_fp16(case):
     _check(L.OP_CONV, case, dt=L.DT_F16)
 
 
+@pytest.mark.parametrize("cin,cout,k,s", [(34, 64, 3, 2), (34, 256, 3, 1), (33, 33, 3, 1), (34, 64, 1, 1)])
+def test_conv_tc_k_padded_by_tma_oob(cin, cout, k, s):
+    """The engine feeds 33/34-channel tensors (48-wide buffers) as ONE 64-channel K chunk: channels
+    48..63 do not exist in memory and must come back as TMA out-of-bounds zeros."""
+    got, exp, pad_ok = run_conv_case(L.OP_CONV, 2, 64, 64, cin, cout, k, s, True, False, True, True, False,
+                                     seed=cin + cout, in_stride=48, cin_pad=64)
+    assert pad_ok
+    assert (got - exp).abs().max().item() <= exp.abs().max().item() * 2 ** -8 + 1e-6
+
+
 def test_conv_tc_full_resolution_property():
     """BASELINE-size property check: 64->64 3x3 @128x128, B=8 -- linearity in the input
     (conv(a*x) == a*conv(x) without bias/relu) on the tensor-core path."""
