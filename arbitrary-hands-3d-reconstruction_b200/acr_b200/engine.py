@@ -111,12 +111,26 @@ class Engine:
 
     # ------------------------------------------------------------------ weights
     def _pack_conv(self, sd, blob: _Blob, wkey: str, bnkey: Optional[str], has_bias: bool, cin_pad: int,
-                   cout_pad: int) -> Tuple[int, int]:
+                   cout_pad: int, pair: bool = False) -> Tuple[int, int]:
         w = np.ascontiguousarray(sd[wkey + ".weight"], np.float32)
-        cout, cin, k, _ = w.shape
         cb = np.ascontiguousarray(sd[wkey + ".bias"], np.float32) if has_bias else None
         bn = [np.ascontiguousarray(sd[f"{bnkey}.{n}"], np.float32) for n in
               ("weight", "bias", "running_mean", "running_var")] if bnkey else [None] * 4
+        if pair:
+            # x-paired grid: channel index = dx*32 + c.  Output pixel x_out = 2j+dxo reads input pixel
+            # x_in = 2(j+pt-1)+dxi through the original tap kx = x_in - x_out + 1 (zero block if outside 0..2)
+            co, ci = w.shape[:2]
+            w2 = np.zeros((2 * co, 2 * ci, 3, 3), np.float32)
+            for dxo in range(2):
+                for dxi in range(2):
+                    for pt in range(3):
+                        kx = 2 * (pt - 1) + dxi - dxo + 1
+                        if 0 <= kx <= 2:
+                            w2[dxo * co:(dxo + 1) * co, dxi * ci:(dxi + 1) * ci, :, pt] = w[:, :, :, kx]
+            w = w2
+            cb = None if cb is None else np.tile(cb, 2)
+            bn = [None if b is None else np.tile(b, 2) for b in bn]
+        cout, cin, k, _ = w.shape
         wp = np.zeros((cout_pad, k * k, cin_pad), np.uint16)
         bias = np.zeros(cout_pad, np.float32)
         p = lambda a: None if a is None else a.ctypes.data
@@ -221,14 +235,26 @@ class Engine:
         if self.dry_run:
             return
 
-        def ctensor(t: Tensor) -> L.Tensor:
+        def ctensor(t: Tensor, pair: bool = False) -> L.Tensor:
             g = geom(t)
             ct = L.Tensor()
             ext = t.dtype == "u8"
             ct.offset = 0 if ext else g["offset"] + (t.c_off * g["esz"] if t.base is not None else 0)
             ct.C, ct.H, ct.W = t.C, t.H, t.W
             ct.pix_stride, ct.dtype, ct.external = g["stride"], g["dt"], int(ext)
+            if pair:   # dense 32-channel NHWC seen as (H, W/2, 64): two x-adjacent pixels form one 128-byte row
+                assert t.base is None and g["stride"] == t.C == 32 and t.W % 2 == 0
+                ct.C, ct.W, ct.pix_stride = 64, t.W // 2, 64
             return ct
+
+        def pairable(r) -> bool:
+            """3x3 stride-1 32->32 convs on dense tensors run as 64->64 convs on the x-paired grid: same
+            bytes in memory, but 128-byte operand rows (SWIZZLE_128B) instead of 64-byte ones."""
+            a = r.get("attrs", {})
+            if r["kind"] not in (L.OP_CONV, L.OP_CONV_REF) or "fold_side" in a or a.get("k") != 3 or a.get("s") != 1:
+                return False
+            ts = r["ins"] + [r["out"]]
+            return all(t.C == 32 and t.base is None and t.dtype == "act" and t.W % 32 == 0 for t in ts)
 
         # ---- weights + C op records
         f32 = lambda k: np.ascontiguousarray(sd[k], np.float32)
@@ -236,10 +262,11 @@ class Engine:
         for i, r in enumerate(recs):
             o = cops[i]
             o.kind = r["kind"]
-            o.out = ctensor(r["out"])
+            pair = pairable(r)
+            o.out = ctensor(r["out"], pair)
             o.n_in = len(r["ins"])
             for j, t in enumerate(r["ins"]):
-                o.in_[j] = ctensor(t)
+                o.in_[j] = ctensor(t, pair)
             for j, t in enumerate(r.get("aux", [])):
                 o.aux[j] = ctensor(t)
             a = r.get("attrs", {})
@@ -261,6 +288,9 @@ class Engine:
                     o.cin_pad = 128
                     o.w_offset[0] = self._pack_raw(blob, weff, o.cin_pad, o.cout_pad)
                     o.shift[0] = 1      # ACR_CONV_BIAS_PER_IMAGE (aux[0] = bias_img from the part head)
+                elif pair:
+                    o.cin_pad = o.cout_pad = 64
+                    o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, 64, pair=True)
                 else:
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
                     if a.get("pow11"):

@@ -76,3 +76,48 @@ def test_conv_tc_full_resolution_property():
     c1 = (8, 128, 128, 64, 64, 3, 1, False, False, False, False, True)
     g1, e1, _ = run_conv_case(L.OP_CONV, *c1, seed=11)
     assert (g1 - e1).abs().max().item() <= e1.abs().max().item() * 2e-5 + 1e-6
+
+
+def test_conv_tc_x_paired_32ch():
+    """The engine runs dense 32->32 3x3 convs as 64->64 convs on the x-paired grid (two adjacent pixels =
+    one 128-byte operand row).  Packed through Engine._pack_conv(pair=True); expected from the ORIGINAL
+    weights with plain fp32 conv + BN + residual + ReLU."""
+    import ctypes as C
+    import torch.nn.functional as Fn
+    from acr_b200.engine import Engine, _Blob
+    from tests.helpers import ctensor, rup
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 2, 32, 64
+    x = torch.randn(B, 32, H, W, generator=g).bfloat16()
+    res = torch.randn(B, 32, H, W, generator=g).bfloat16()
+    sd = {"c.weight": torch.randn(32, 32, 3, 3, generator=g) * (2 / 288) ** 0.5,
+          "b.weight": torch.rand(32, generator=g) + 0.5, "b.bias": torch.randn(32, generator=g) * 0.1,
+          "b.running_mean": torch.randn(32, generator=g) * 0.1, "b.running_var": torch.rand(32, generator=g) + 0.5}
+    eng = Engine(None, B, "cpu", dry_run=True)
+    blob = _Blob()
+    w_off, b_off = eng._pack_conv({k: v.numpy() for k, v in sd.items()}, blob, "c", "b", False, 64, 64, pair=True)
+    xin = x.permute(0, 2, 3, 1).contiguous()          # NHWC, C=32 dense
+    rin = res.permute(0, 2, 3, 1).contiguous()
+    nbytes = xin.numel() * 2
+    arena = torch.zeros(3 * rup(nbytes, 1024), dtype=torch.uint8)
+    arena[:nbytes] = xin.view(torch.uint8).flatten()
+    arena[rup(nbytes, 1024): rup(nbytes, 1024) + nbytes] = rin.view(torch.uint8).flatten()
+    op = L.Op()
+    op.kind, op.n_in = L.OP_CONV, 2
+    op.in_[0] = ctensor(0, 64, H, W // 2, 64, L.DT_BF16)
+    op.in_[1] = ctensor(rup(nbytes, 1024), 64, H, W // 2, 64, L.DT_BF16)
+    op.out = ctensor(2 * rup(nbytes, 1024), 64, H, W // 2, 64, L.DT_BF16)
+    op.w_offset[0], op.w_offset[1] = w_off, b_off
+    op.k, op.stride, op.relu, op.has_residual, op.cin_pad, op.cout_pad = 3, 1, 1, 1, 64, 64
+    d_arena = arena.cuda()
+    d_blob = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).cuda()
+    L.check(L.load().acr_b200_run_op(C.byref(op), B, d_arena.data_ptr(), d_blob.data_ptr(), None, L.DT_BF16,
+                                     torch.cuda.current_stream().cuda_stream), "run_op")
+    torch.cuda.synchronize()
+    got = d_arena[2 * rup(nbytes, 1024): 2 * rup(nbytes, 1024) + nbytes].cpu().view(torch.bfloat16)
+    got = got.view(B, H, W, 32).permute(0, 3, 1, 2).float()
+    sc = sd["b.weight"] / torch.sqrt(sd["b.running_var"] + 1e-5)
+    exp = Fn.conv2d(x.float(), sd["c.weight"], None, 1, 1) * sc.view(1, -1, 1, 1) \
+        + (sd["b.bias"] - sd["b.running_mean"] * sc).view(1, -1, 1, 1) + res.float()
+    exp = torch.relu(exp)
+    assert (got - exp).abs().max().item() <= exp.abs().max().item() * 2 ** -6   # weights are rounded to bf16 here
