@@ -31,7 +31,7 @@ _DEFAULTS = dict(
     temporal_optimization=False, smooth_coeff=4.0,         # config.py:29-30
     model_path=os.path.join(project_dir, "checkpoints", "wild.pkl"),
     mano_root=os.path.join(project_dir, "mano"),           # acr/mano_wrapper.py:22 uses 'mano/'
-    cam_trans_mode="none",                                 # 'none' | 'lstsq' (device) -- SURVEY 8f-1
+    cam_trans_mode="lstsq",                                # 'lstsq' (device least squares) | 'none'
     return_maps=True,                                      # materialise NCHW fp32 maps lazily on access
     demo_mode="image", inputs=None, output_dir=None, save_dict_results=False,
 )

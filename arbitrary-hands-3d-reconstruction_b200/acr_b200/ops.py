@@ -61,6 +61,19 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
     return out
 
 
+def cam_trans(j3d: torch.Tensor, pj2d: torch.Tensor, focal_length: float = 1265.0, img_size: float = 512.0,
+              n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(n,21,3), (n,21,2) -> (n,3) camera translation (closed-form least squares on the device)."""
+    L.require_cuda(j3d, pj2d, n_dev)
+    n = j3d.shape[0]
+    out = torch.empty(n, 3, device=j3d.device)
+    if n:
+        L.check(L.load().acr_b200_cam_trans(L.ptr(j3d.contiguous().float()), L.ptr(pj2d.contiguous().float()),
+                                            L.ptr(n_dev), n, float(focal_length), float(img_size), L.ptr(out),
+                                            L.current_stream()), "cam_trans")
+    return out
+
+
 # ------------------------------------------------------------------------------ rotations
 def rot6d_to_aa(rot6d: torch.Tensor) -> torch.Tensor:
     """(N, 6*J) -> (N, 3*J); drop-in for acr.utils.rot6D_to_angular."""

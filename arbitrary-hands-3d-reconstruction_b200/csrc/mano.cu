@@ -274,6 +274,39 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
   }
 }
 
+// estimate_translation_np (acr/utils.py:430-472) for one hand per thread, fp64 like the numpy original:
+// rows [f,0,cx-u | (u-cx)*Z - f*X] and [0,f,cy-v | (v-cy)*Z - f*Y] of every usable joint, normal equations.
+__global__ void cam_trans_kernel(const float* __restrict__ j3d, const float* __restrict__ pj2d,
+                                 const int32_t* __restrict__ n_dev, int n_max, float focal, float img_size,
+                                 float* __restrict__ out) {
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = focal, c0 = (double)(img_size * 0.5f);
+  double A00 = 0, A01 = 0, A02 = 0, A11 = 0, A12 = 0, A22 = 0, b0 = 0, b1 = 0, b2 = 0;
+  int used = 0;
+  for (int j = 0; j < 21; ++j) {
+    const float X = j3d[((size_t)i * 21 + j) * 3 + 0], Y = j3d[((size_t)i * 21 + j) * 3 + 1], Z = j3d[((size_t)i * 21 + j) * 3 + 2];
+    const float u = (pj2d[((size_t)i * 21 + j) * 2 + 0] + 1.f) * (img_size * 0.5f);
+    const float v = (pj2d[((size_t)i * 21 + j) * 2 + 1] + 1.f) * (img_size * 0.5f);
+    if (!(v > -2.f) || Z == -2.f) continue;   // the reference's "confidence" tests (acr/utils.py:489-492)
+    ++used;
+    const double qx = c0 - (double)u, qy = c0 - (double)v;        // third column of the two rows
+    const double cx = ((double)u - c0) * (double)Z - f * (double)X, cy = ((double)v - c0) * (double)Z - f * (double)Y;
+    A00 += f * f; A02 += f * qx; b0 += f * cx;
+    A11 += f * f; A12 += f * qy; b1 += f * cy;
+    A22 += qx * qx + qy * qy; b2 += qx * cx + qy * cy;
+  }
+  float* o = out + (size_t)i * 3;
+  if (used < 4) { o[0] = o[1] = o[2] = -1.f; return; }
+  // symmetric 3x3 solve (A01 = 0): Cramer's rule in fp64
+  const double det = A00 * (A11 * A22 - A12 * A12) - A01 * (A01 * A22 - A12 * A02) + A02 * (A01 * A12 - A11 * A02);
+  const double d0 = b0 * (A11 * A22 - A12 * A12) - A01 * (b1 * A22 - A12 * b2) + A02 * (b1 * A12 - A11 * b2);
+  const double d1 = A00 * (b1 * A22 - A12 * b2) - b0 * (A01 * A22 - A12 * A02) + A02 * (A01 * b2 - b1 * A02);
+  const double d2 = A00 * (A11 * b2 - b1 * A12) - A01 * (A01 * b2 - b1 * A02) + b0 * (A01 * A12 - A11 * A02);
+  o[0] = (float)(d0 / det); o[1] = (float)(d1 / det); o[2] = (float)(d2 / det);
+}
+
 __global__ void rodrigues_kernel(const float* __restrict__ aa, int n, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -362,6 +395,15 @@ extern "C" int acr_b200_mano_forward(const float* model_l, const float* model_r,
   p.pj2d_org = pj2d_org;
   dim3 grid(ceil_div(n_max, HG), ceil_div(NV, VPB));
   mano_forward_kernel<<<grid, VPB, 0, (cudaStream_t)stream>>>(p);
+  ACR_CHECK_LAUNCH();
+  return ACR_B200_OK;
+}
+
+extern "C" int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max,
+                                  float focal_length, float img_size, float* cam_trans, void* stream) {
+  ACR_CHECK_ARG(n_max >= 0 && (n_max == 0 || (j3d && pj2d && cam_trans)), "cam_trans: bad arguments");
+  if (n_max == 0) return ACR_B200_OK;
+  cam_trans_kernel<<<ceil_div(n_max, 128), 128, 0, (cudaStream_t)stream>>>(j3d, pj2d, n_dev, n_max, focal_length, img_size, cam_trans);
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }

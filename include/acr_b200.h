@@ -62,6 +62,15 @@ int acr_b200_mano_forward(const float* model_l, const float* model_r, const floa
                           const float* offsets, float* verts, float* joints, float* center,
                           float* verts_camed, float* pj2d, float* pj2d_org, void* stream);
 
+/* Camera translation of every hand from its 21 joints: the closed-form weighted least squares of
+ * estimate_translation_np (acr/utils.py:430-472) -- the reference's own fall-back for the host-side
+ * cv2.solvePnPRansac loop (estimate_translation :474-519, called from vertices_kp3d_projection :403-407,
+ * SURVEY.md 8f-1).  joints_2d = (pj2d+1)*img_size/2 as in :404; a joint is used iff its pixel y > -2
+ * and its z != -2 (:489-492); fewer than 4 usable joints -> (-1,-1,-1).  fp64 normal equations.
+ * j3d (n,21,3), pj2d (n,21,2) -> cam_trans (n,3).  n_dev as in acr_b200_mano_forward.              */
+int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max, float focal_length,
+                       float img_size, float* cam_trans, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Rotations
  * ---------------------------------------------------------------------------------------- */

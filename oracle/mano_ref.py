@@ -114,6 +114,32 @@ def project(verts, j3d, cam, offsets=None):
     return out
 
 
+def cam_trans_lstsq(j3d, pj2d, focal_length=1265.0, img_size=512.0):
+    """Closed-form camera translation per hand: estimate_translation_np (acr/utils.py:430-472) with the
+    joint-validity tests of estimate_translation (:489-500): pixel y > -2 and z != -2; <4 valid -> (-1,-1,-1)
+    (ROMP's INVALID_TRANS; the reference's own constant is undefined, :425,504).  float64 like numpy."""
+    j3d = np.asarray(j3d, F)
+    j2d = ((np.asarray(pj2d, F) + 1) * F(img_size / 2)).astype(F)       # acr/utils.py:404
+    out = np.zeros((j3d.shape[0], 3), np.float64)
+    f = np.array([focal_length, focal_length], np.float64)
+    center = np.array([img_size / 2.0, img_size / 2.0])
+    for i in range(j3d.shape[0]):
+        m = (j2d[i, :, -1] > -2.0) & (j3d[i, :, -1] != -2.0)
+        if m.sum() < 4:
+            out[i] = -1
+            continue
+        S, J = j3d[i][m], j2d[i][m]
+        n = S.shape[0]
+        Z = np.reshape(np.tile(S[:, 2], (2, 1)).T, -1)
+        XY = np.reshape(S[:, 0:2], -1)
+        O = np.tile(center, n)
+        Fv = np.tile(f, n)
+        Q = np.array([Fv * np.tile(np.array([1, 0]), n), Fv * np.tile(np.array([0, 1]), n), O - np.reshape(J, -1)]).T
+        c = (np.reshape(J, -1) - O) * Z - Fv * XY
+        out[i] = np.linalg.solve(Q.T @ Q, Q.T @ c)
+    return out.astype(F)
+
+
 def mano_wrapper_forward(assets, poses, betas, L, R, cam=None, offsets=None):
     """MANOWrapper.forward: rows [:L] go through the left layer, [L:L+R] through the
     right one; results concatenated left-first (acr/mano_wrapper.py:40-48)."""

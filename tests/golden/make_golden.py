@@ -24,8 +24,12 @@ REF = "/root/reference"
 
 def import_reference():
     sys.argv = ["make_golden"]
-    sys.path.insert(0, PKG)        # for acr_b200.* only
-    sys.path.insert(0, REF)        # reference's acr / mano win the name lookup
+    # our package dir also contains drop-in `acr` / `mano` packages (regular packages would shadow the
+    # reference's namespace package `mano`), so it is on sys.path only while acr_b200.synth is imported
+    sys.path.insert(0, PKG)
+    import acr_b200.synth  # noqa: F401
+    sys.path.remove(PKG)
+    sys.path.insert(0, REF)
     os.chdir(REF)
     for name in ("h5py", "imgaug", "imgaug.augmenters", "chumpy", "chumpy.ch"):
         sys.modules.setdefault(name, types.ModuleType(name))
@@ -111,9 +115,17 @@ def main():
         vc = ref_utils.batch_orth_proj(verts, torch.from_numpy(cam), mode="3d", keep_dim=True)
         pj = ref_utils.batch_orth_proj(j3d, torch.from_numpy(cam), mode="2d")[:, :, :2]
         pjo = ref_utils.convert_kp2d_from_input_to_orgimg(pj, torch.from_numpy(offsets))
+    # camera translation: the reference's closed-form estimator (its fall-back for cv2.solvePnPRansac),
+    # called exactly like estimate_translation does (acr/utils.py:404-406, 489-517)
+    j3d_np, j2d_np = j3d.numpy(), (pj.numpy() + 1) * 256
+    ct = np.zeros((n, 3), np.float32)
+    for i in range(n):
+        m = (j2d_np[i, :, -1] > -2.) * (j3d_np[i, :, -1] != -2.)
+        ct[i] = ref_utils.estimate_translation_np(j3d_np[i][m], j2d_np[i][m], m[m].astype(np.float32),
+                                                  focal_length=1265, img_size=np.array([512., 512.]))
     np.savez_compressed(os.path.join(HERE, "mano_golden.npz"), poses=poses, betas=betas, cam=cam, offsets=offsets,
                         L=L, R=R, verts=verts.numpy(), j3d=j3d.numpy(), center=torch.cat([lc, rc]).numpy(),
-                        verts_camed=vc.numpy(), pj2d=pj.numpy(), pj2d_org=pjo.numpy())
+                        verts_camed=vc.numpy(), pj2d=pj.numpy(), pj2d_org=pjo.numpy(), cam_trans=ct)
 
     # ------------------------------------------------------------- parser on synthetic maps
     from acr.result_parser import ResultParser

@@ -65,6 +65,8 @@ def test_mano_golden(wrapper):
         assert rel_err(out[k].cpu().numpy(), g[gk]) < TOL, k
     assert np.abs(out["verts"].cpu().numpy() - g["verts"]).max() < 3e-6
     assert out["output_hand_type"].tolist() == [0] * L + [1] * R
+    # camera translation (device least squares) vs the reference's estimate_translation_np
+    assert rel_err(out["cam_trans"].cpu().numpy(), g["cam_trans"]) < TOL
 
 
 def test_manolayer_dropin_single_side(assets):

@@ -39,6 +39,8 @@ def test_mano_forward_and_projection(golden_dir):
     for k in ("verts", "j3d", "verts_camed", "pj2d", "pj2d_org"):
         assert _rel(out[k], g[k]) < TOL, k
     assert np.abs(out["verts"] - g["verts"]).max() < 2e-6   # metres
+    ct = mano_ref.cam_trans_lstsq(g["j3d"], g["pj2d"])
+    assert _rel(ct, g["cam_trans"]) < TOL
 
 
 @pytest.mark.parametrize("case", ["both", "no_left", "mixed", "none", "far"])
