@@ -259,12 +259,20 @@ def run_b200(args):
     n_hands = int(bufs.counts[2])
     if rank == 0:
         peaks = load_peaks()
+        traffic = None
+        try:   # DRAM bytes of the conv launch set from the committed ncu capture (same batch / build family)
+            with open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")) as f:
+                tj = json.load(f)
+            if B == 256:
+                traffic = tj["traffic_bytes"]
+        except Exception:
+            pass
         conv_gflop = sum(2.0 * o.out.H * o.out.W * o.out.C * o.ins[0].C * o.attrs["k"] ** 2
                          for o in eng.spec.ops if o.kind == "conv") / 1e9
         ach = conv_gflop * B / conv_ms if conv_ms else 0.0          # TFLOP/s (GFLOP/ms)
         img_s = world * B * args.steps / (ms_value / 1e3)
         e2e_s = world * B * args.steps / (ms_e2e / 1e3)
-        launches = eng.num_launches + 3 + 1
+        launches = eng.num_launches + 3 + 1 + (1 if cfg_args().cam_trans_mode == "lstsq" else 0)
         out = {
             "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
@@ -279,9 +287,11 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(frames_host.numel()),
                     "d2h_bytes_per_step": int(verts_host.numel() * 4 + counts_host.numel() * 4)},
             "gpu_launches": launches * args.steps,
-            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all 344 launches of a step)",
+            "roofline": {"kernel": f"conv_tc_kernel (tcgen05 implicit-GEMM conv, all {conv_n} launches of a step)",
                          "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["tf_sustained"] if ach else 0.0, "traffic": None,
+                         "frac": ach / peaks["tf_sustained"] if ach else 0.0, "traffic": traffic,
+                         "traffic_note": "DRAM read+write bytes of the whole conv launch set per step, ncu capture "
+                                         "profiles/r1_conv_traffic.json (algorithmic: 163.5 GB)",
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "algorithmic_gflop_per_launch_set": conv_gflop * B,
                          "conv_ms_per_step": conv_ms, "conv_share_of_plan": conv_ms / total_prof_ms if total_prof_ms else None,
