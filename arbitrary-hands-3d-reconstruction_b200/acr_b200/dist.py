@@ -40,3 +40,40 @@ def compact_gathered(gathered: torch.Tensor, counts: torch.Tensor) -> List[torch
     """Valid rows of every rank's shard, in rank order (counts[:, 2] = L+R of each shard)."""
     n = counts[:, 2].tolist()
     return [gathered[r, : int(n[r])] for r in range(gathered.shape[0])]
+
+
+class PeerVertexGather:
+    """Vertex all-gather fused into the MANO kernel: a symmetric-memory buffer (world, R, 778, 3) whose peer
+    addresses (and, with NVLS, its multicast address) are handed to ``acr_b200_mano_forward_gather``; the
+    kernel's epilogue stores every vertex into all ranks' buffers over NVLink (``multimem.st`` through the
+    NVSwitch when multicast is available, per-peer stores otherwise).  ``finish()`` is the cross-rank barrier
+    that makes the stores of all ranks visible (symmetric-memory signal pads, enqueued on the current stream)."""
+
+    def __init__(self, rows: int, device, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.rows = int(rows)
+        self.buf = symm_mem.empty((self.world, self.rows, 778, 3), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = 0
+        if use_multicast:
+            try:
+                if self.hdl.has_multicast_support:
+                    mc = int(self.hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        self.multicast_ptr = mc
+        self.dst_row_offset = self.rank * self.rows
+
+    @property
+    def mode(self) -> str:
+        return "multimem.st (NVLS multicast)" if self.multicast_ptr else "peer stores"
+
+    def finish(self) -> None:
+        self.hdl.barrier(channel=0)
+
+    def gathered(self) -> torch.Tensor:
+        return self.buf

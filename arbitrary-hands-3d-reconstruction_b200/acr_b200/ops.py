@@ -30,8 +30,9 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
                  betas: torch.Tensor, hand_type: Optional[torch.Tensor] = None, default_side: int = 1,
                  center_idx: Optional[int] = 9, cam: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
-                 want_camed: bool = True):
-    """-> dict(verts, joints, center[, verts_camed, pj2d, pj2d_org]); all (n, ...) fp32 CUDA tensors."""
+                 want_camed: bool = True, peers=None):
+    """-> dict(verts, joints, center[, verts_camed, pj2d, pj2d_org]); all (n, ...) fp32 CUDA tensors.
+    ``peers`` (acr_b200.dist.PeerVertexGather) fuses the cross-GPU vertex all-gather into the kernel."""
     L.require_cuda(poses, betas, hand_type, cam, offsets, n_dev)
     n = poses.shape[0]
     dev = poses.device
@@ -52,11 +53,19 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
     if n == 0:
         return out
     lib = L.load()
-    rc = lib.acr_b200_mano_forward(L.ptr(model_l), L.ptr(model_r), L.ptr(poses), L.ptr(betas), L.ptr(hand_type),
-                                   int(default_side), L.ptr(n_dev), n, -1 if center_idx is None else int(center_idx),
-                                   L.ptr(cam), L.ptr(offsets), L.ptr(out["verts"]), L.ptr(out["joints"]),
-                                   L.ptr(out["center"]), L.ptr(out.get("verts_camed")), L.ptr(out.get("pj2d")),
-                                   L.ptr(out.get("pj2d_org")), L.current_stream())
+    common = (L.ptr(model_l), L.ptr(model_r), L.ptr(poses), L.ptr(betas), L.ptr(hand_type),
+              int(default_side), L.ptr(n_dev), n, -1 if center_idx is None else int(center_idx),
+              L.ptr(cam), L.ptr(offsets), L.ptr(out["verts"]), L.ptr(out["joints"]),
+              L.ptr(out["center"]), L.ptr(out.get("verts_camed")), L.ptr(out.get("pj2d")),
+              L.ptr(out.get("pj2d_org")))
+    if peers is None:
+        rc = lib.acr_b200_mano_forward(*common, L.current_stream())
+    else:
+        assert n <= peers.rows, "gather buffer too small"
+        import ctypes as C
+        arr = (C.c_uint64 * len(peers.peer_ptrs))(*peers.peer_ptrs)
+        rc = lib.acr_b200_mano_forward_gather(*common, C.cast(arr, C.c_void_p), len(peers.peer_ptrs),
+                                              int(peers.multicast_ptr), int(peers.dst_row_offset), L.current_stream())
     L.check(rc, "mano_forward")
     return out
 

@@ -53,7 +53,17 @@ struct ManoParams {
   float* verts_camed;
   float* pj2d;
   float* pj2d_org;
+  // fused vertex all-gather (acr_b200_mano_forward_gather)
+  float* peer_verts[8];
+  float* mc_verts;      // NVLS multicast address of the gather buffer, or nullptr
+  int n_peers;
+  long long dst_row;    // first row of this rank's block inside every gather buffer
 };
+
+// one value to every GPU of the multicast group: the NVSwitch replicates the store (NVLS)
+__device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
 
 struct ProjCtx {  // per-hand projection constants kept in shared memory
   float s, tx, ty, padw, padh, ltx, lty;
@@ -265,6 +275,16 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
         float* o = p.verts + ((size_t)hand * NV + v) * 3;
         o[0] = x; o[1] = y; o[2] = z;
       }
+      if (p.mc_verts) {          // fused all-gather, one multimem store per value
+        float* o = p.mc_verts + ((size_t)(p.dst_row + hand) * NV + v) * 3;
+        multimem_st_f32(o, x); multimem_st_f32(o + 1, y); multimem_st_f32(o + 2, z);
+      } else if (p.n_peers > 0) {  // fused all-gather, peer stores over NVLink
+        const size_t idx = ((size_t)(p.dst_row + hand) * NV + v) * 3;
+        for (int r = 0; r < p.n_peers; ++r) {
+          float* o = p.peer_verts[r] + idx;
+          o[0] = x; o[1] = y; o[2] = z;
+        }
+      }
       if (p.verts_camed && p.cam) {
         float* o = p.verts_camed + ((size_t)hand * NV + v) * 3;
         o[0] = x * s_pc[h].s + s_pc[h].tx; o[1] = y * s_pc[h].s + s_pc[h].ty; o[2] = z;
@@ -365,11 +385,12 @@ extern "C" int acr_b200_mano_pack_model(const float* shapedirs, const float* pos
   return ACR_B200_OK;
 }
 
-extern "C" int acr_b200_mano_forward(const float* model_l, const float* model_r, const float* poses,
-                                     const float* betas, const int32_t* hand_type, int default_side,
-                                     const int32_t* n_dev, int n_max, int center_idx, const float* cam,
-                                     const float* offsets, float* verts, float* joints, float* center,
-                                     float* verts_camed, float* pj2d, float* pj2d_org, void* stream) {
+static int mano_forward_impl(const float* model_l, const float* model_r, const float* poses,
+                             const float* betas, const int32_t* hand_type, int default_side,
+                             const int32_t* n_dev, int n_max, int center_idx, const float* cam,
+                             const float* offsets, float* verts, float* joints, float* center,
+                             float* verts_camed, float* pj2d, float* pj2d_org, const uint64_t* peer_ptrs, int n_peers,
+                             uint64_t multicast_ptr, int64_t dst_row_offset, void* stream) {
   ACR_CHECK_ARG(n_max >= 0, "mano_forward: n_max < 0");
   if (n_max == 0) return ACR_B200_OK;
   ACR_CHECK_ARG(poses && betas, "mano_forward: poses/betas are null");
@@ -393,10 +414,37 @@ extern "C" int acr_b200_mano_forward(const float* model_l, const float* model_r,
   p.n_dev = n_dev; p.n_max = n_max; p.center_src = center_src; p.cam = cam; p.offsets = offsets;
   p.verts = verts; p.joints = joints; p.center = center; p.verts_camed = verts_camed; p.pj2d = pj2d;
   p.pj2d_org = pj2d_org;
+  ACR_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_ptrs || multicast_ptr), "mano_forward_gather: bad peer list");
+  p.n_peers = multicast_ptr ? 0 : n_peers;
+  p.mc_verts = reinterpret_cast<float*>(multicast_ptr);
+  p.dst_row = dst_row_offset;
+  for (int r = 0; r < 8; ++r) p.peer_verts[r] = (peer_ptrs && r < n_peers) ? reinterpret_cast<float*>(peer_ptrs[r]) : nullptr;
   dim3 grid(ceil_div(n_max, HG), ceil_div(NV, VPB));
   mano_forward_kernel<<<grid, VPB, 0, (cudaStream_t)stream>>>(p);
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
+}
+
+extern "C" int acr_b200_mano_forward(const float* model_l, const float* model_r, const float* poses,
+                                     const float* betas, const int32_t* hand_type, int default_side,
+                                     const int32_t* n_dev, int n_max, int center_idx, const float* cam,
+                                     const float* offsets, float* verts, float* joints, float* center,
+                                     float* verts_camed, float* pj2d, float* pj2d_org, void* stream) {
+  return mano_forward_impl(model_l, model_r, poses, betas, hand_type, default_side, n_dev, n_max, center_idx, cam,
+                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, const float* poses,
+                                            const float* betas, const int32_t* hand_type, int default_side,
+                                            const int32_t* n_dev, int n_max, int center_idx, const float* cam,
+                                            const float* offsets, float* verts, float* joints, float* center,
+                                            float* verts_camed, float* pj2d, float* pj2d_org,
+                                            const uint64_t* peer_ptrs, int n_peers, uint64_t multicast_ptr,
+                                            int64_t dst_row_offset, void* stream) {
+  ACR_CHECK_ARG(n_peers > 0, "mano_forward_gather: n_peers must be positive");
+  return mano_forward_impl(model_l, model_r, poses, betas, hand_type, default_side, n_dev, n_max, center_idx, cam,
+                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, peer_ptrs, n_peers,
+                           multicast_ptr, dst_row_offset, stream);
 }
 
 extern "C" int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max,

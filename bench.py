@@ -173,16 +173,32 @@ def run_b200(args):
     frames_host = torch.randint(0, 256, (B, 512, 512, 3), generator=gi, dtype=torch.uint8).pin_memory()
     frames_dev = frames_host.to(dev)
     offsets = torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]], device=dev).repeat(B, 1)
-    from acr_b200.dist import gather_vertices
-    gather_buf = torch.empty(world, 2 * B, 778, 3, device=dev) if world > 1 else None
-    gather_cnt = torch.empty(world, 8, dtype=torch.int32, device=dev) if world > 1 else None
+    from acr_b200.dist import PeerVertexGather, gather_vertices
+    gather_buf = gather_cnt = peers = None
+    gather_mode = "single GPU"
+    if world > 1:
+        gather_cnt = torch.empty(world, 8, dtype=torch.int32, device=dev)
+        if args.gather == "fused":
+            try:   # vertex all-gather fused into the MANO kernel (multimem.st / peer stores over NVLink)
+                peers = PeerVertexGather(2 * B, dev)
+                gather_mode = f"vertex all-gather fused into mano_forward_kernel: {peers.mode} over NVLink + symmetric-memory barrier"
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] symmetric memory unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+        if peers is None:
+            gather_buf = torch.empty(world, 2 * B, 778, 3, device=dev)
+            gather_mode = "1 NCCL all-gather of the vertices"
     verts_host = torch.empty(2 * B, 778, 3).pin_memory()
     counts_host = torch.empty(8, dtype=torch.int32).pin_memory()
 
     def step(frames):
-        bufs, mano = app.fused_forward(frames, offsets)
-        if world > 1:   # the one collective of the path: vertices of every shard on every rank (NVLink)
-            gather_vertices(mano["verts"], bufs.counts, gather_buf, gather_cnt)
+        bufs, mano = app.fused_forward(frames, offsets, peers=peers)
+        if world > 1:   # the one exchange of the path: vertices of every shard on every rank (NVLink)
+            if peers is not None:
+                peers.finish()                                         # cross-rank barrier, stores have landed
+                dist.all_gather_into_tensor(gather_cnt.view(-1), bufs.counts)   # 32 B of row counts
+            else:
+                gather_vertices(mano["verts"], bufs.counts, gather_buf, gather_cnt)
         return bufs, mano
 
     def sync_all():
@@ -279,7 +295,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"batch {B}/GPU, 512x512 uint8 RGB, HRNet-W32, two-hand MANO (BASELINE configs[2])",
                        "global_batch": B * world, "hands_per_step_rank0": n_hands,
-                       "parallelism": f"frames sharded over {world} rank(s), 1 NCCL all-gather of verts" if world > 1 else "single GPU",
+                       "parallelism": f"frames sharded over {world} rank(s); {gather_mode}" if world > 1 else "single GPU",
                        "l2_hygiene": f"inputs {B * 786432 / 2**20:.0f} MiB + {eng.arena_bytes / 2**20:.0f} MiB activations per step >> 126 MB L2",
                        "weights": "seeded synthetic (no checkpoint ships with the reference)"},
             "clocks": clocks,
@@ -345,6 +361,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--ref-batch", type=int, default=8, help="frames per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: vertex all-gather fused into the MANO kernel (symmetric memory) or a separate NCCL call")
     args = ap.parse_args()
     if args.gpus > 1:
         args.cpu_baseline = False

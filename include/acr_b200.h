@@ -62,6 +62,22 @@ int acr_b200_mano_forward(const float* model_l, const float* model_r, const floa
                           const float* offsets, float* verts, float* joints, float* center,
                           float* verts_camed, float* pj2d, float* pj2d_org, void* stream);
 
+/* Same kernel, with the vertex all-gather FUSED into its epilogue: besides the local `verts`, every
+ * vertex is stored straight into the gather buffers of all ranks over NVLink -- either with one
+ * `multimem.st` per value through `multicast_ptr` (NVSwitch in-fabric broadcast, NVLS) or, when that is 0,
+ * with one peer store per rank through `peer_ptrs[0..n_peers)` (HOST array of device addresses obtained
+ * from symmetric memory / CUDA IPC).  Row r of this rank lands at row `dst_row_offset + r` of every
+ * gather buffer ((world*R, 778, 3) fp32).  Replaces the gather step of nn.DataParallel
+ * (acr/main.py:61) / the separate ncclAllGather of SURVEY.md 8e.  The caller provides the cross-rank
+ * barrier after the launch (e.g. the symmetric-memory barrier on the same stream).                    */
+int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, const float* poses,
+                                 const float* betas, const int32_t* hand_type, int default_side,
+                                 const int32_t* n_dev, int n_max, int center_idx, const float* cam,
+                                 const float* offsets, float* verts, float* joints, float* center,
+                                 float* verts_camed, float* pj2d, float* pj2d_org,
+                                 const uint64_t* peer_ptrs, int n_peers, uint64_t multicast_ptr,
+                                 int64_t dst_row_offset, void* stream);
+
 /* Camera translation of every hand from its 21 joints: the closed-form weighted least squares of
  * estimate_translation_np (acr/utils.py:430-472) -- the reference's own fall-back for the host-side
  * cv2.solvePnPRansac loop (estimate_translation :474-519, called from vertices_kp3d_projection :403-407,
