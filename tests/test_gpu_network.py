@@ -130,3 +130,25 @@ def test_dropin_api_end_to_end(sd, image, precision):
     assert int(bufs.counts[2]) == N
     assert torch.equal(mano["verts"][:N], out["verts"])
     args().model_precision = "bf16"
+
+
+def test_cuda_graph_replay_matches_eager(sd):
+    """acr.main.ACR.capture_graph: one CUDA graph for the ~380 launches of the pipeline (serving / webcam
+    mode, batch 1..few) must reproduce the eager launches bit for bit."""
+    from acr.main import ACR
+    from acr_b200.synth import make_synthetic_mano
+    assets = {"left": make_synthetic_mano("left"), "right": make_synthetic_mano("right")}
+    app = ACR(state_dict=sd, mano_assets=assets)
+    gi = torch.Generator().manual_seed(77)
+    offs = torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]]).cuda()
+    replay = app.capture_graph(1)
+    for _ in range(3):
+        frame = torch.randint(0, 256, (1, 512, 512, 3), generator=gi, dtype=torch.uint8).cuda()
+        bufs, mano = app.fused_forward(frame, offs)
+        torch.cuda.synchronize()
+        n = int(bufs.counts[2])
+        v_eager, p_eager = mano["verts"][:n].clone(), bufs.params_pred[:n].clone()
+        bufs_g, mano_g = replay(frame, offs)
+        torch.cuda.synchronize()
+        assert int(bufs_g.counts[2]) == n
+        assert torch.equal(mano_g["verts"][:n], v_eager) and torch.equal(bufs_g.params_pred[:n], p_eager)
