@@ -25,6 +25,7 @@
 //     in TMEM, double buffered), warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) (ReLU) ->
 //     16-bit / fp32 NHWC) overlapping the next tile's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ops.cuh"
 
@@ -69,6 +70,11 @@ __device__ __forceinline__ bool elect_one_sync() {
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
   return pred != 0;
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialisation attribute may
+// start while its predecessor is still draining; everything that touches the predecessor's outputs (or
+// writes memory the predecessor may still read) comes after pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -220,6 +226,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // let the next kernel of the stream begin its own prologue (barrier init, TMEM alloc, weight loads) as
+  // soon as SMs drain; our own prologue above touched nothing the previous kernel produces
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -232,6 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tma_load_2d(b_base + (uint32_t)i * P.b_block_bytes, &P.tmB, bres_bar, (i / P.cchunks) * P.cin_pad + (i % P.cchunks) * CK, 0);
       }
       __syncwarp();
+      pdl_wait();   // weights are constants; the activations below are the previous kernel's output
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -340,6 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int h = (warp - 2) >> 2;         // which half (accumulator) of the super-tile
     const int r = q * 32 + lane;
     int it = 0;
+    pdl_wait();   // residual / per-image bias reads and every output write wait for the previous kernel
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
       const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
@@ -554,6 +565,12 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   return ACR_B200_OK;
 }
 
+static bool pdl_enabled() {   // ACR_B200_PDL=0 disables programmatic dependent launch (A/B timing, debugging)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ACR_B200_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 template <int CK, typename T>
 static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
   static bool configured = false;
@@ -561,8 +578,13 @@ static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
     ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     configured = true;
   }
-  conv_tc_kernel<CK, T><<<pl->grid, TC_THREADS, pl->smem, st>>>(pl->p);
-  ACR_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ACR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<CK, T>, pl->p));
   return ACR_B200_OK;
 }
 
