@@ -31,6 +31,18 @@ class ACR(nn.Module):
 
     @torch.no_grad()
     def process_results(self, outputs):
+        # temporal optimisation (acr/main.py:69-83): OneEuro filters on poses / betas, one bank per hand type,
+        # applied between parse and MANO -- here one device kernel instead of host-side filter objects
+        if getattr(self, 'temporal_optimization', False):
+            from acr_b200 import ops as _ops
+            pd = outputs['params_dict']
+            assert len(pd['poses']) == 2, 'temporal smoothing streams one frame (two hand slots) at a time'
+            if getattr(self, '_one_euro', None) is None:
+                self._one_euro = _ops.OneEuroState(pd['poses'].device)
+            poses, betas = pd['poses'].contiguous(), pd['betas'].contiguous()
+            _ops.one_euro_smooth(poses, betas, self._one_euro, float(self.smooth_coeff),
+                                 hand_type=outputs['output_hand_type'], detection_flag=outputs['detection_flag_cache'].float())
+            pd['poses'], pd['betas'] = poses, betas
         outputs = self.mano_regression(outputs, outputs['meta_data'])
         return outputs
 

@@ -83,6 +83,29 @@ def cam_trans(j3d: torch.Tensor, pj2d: torch.Tensor, focal_length: float = 1265.
     return out
 
 
+class OneEuroState:
+    """Device-side history of the temporal filter (one bank per hand type); zero = no history."""
+
+    def __init__(self, device):
+        self.state = torch.zeros(int(L.load().acr_b200_one_euro_state_floats()), device=device)
+
+    def reset(self) -> None:
+        self.state.zero_()
+
+
+def one_euro_smooth(poses: torch.Tensor, betas: torch.Tensor, state: OneEuroState, smooth_coeff: float = 4.0,
+                    hand_type: Optional[torch.Tensor] = None, detection_flag: Optional[torch.Tensor] = None,
+                    n_dev: Optional[torch.Tensor] = None) -> None:
+    """In-place temporal smoothing of (n,48) poses and (n,10) betas (drop-in for acr.utils.smooth_results
+    applied per hand as in acr/main.py:69-83)."""
+    L.require_cuda(poses, betas, hand_type, detection_flag, n_dev)
+    assert poses.is_contiguous() and betas.is_contiguous() and poses.dtype == betas.dtype == torch.float32
+    if poses.shape[0]:
+        L.check(L.load().acr_b200_one_euro_smooth(L.ptr(poses), L.ptr(betas), L.ptr(hand_type), L.ptr(detection_flag),
+                                                  L.ptr(n_dev), poses.shape[0], L.ptr(state.state), float(smooth_coeff),
+                                                  L.current_stream()), "one_euro_smooth")
+
+
 # ------------------------------------------------------------------------------ rotations
 def rot6d_to_aa(rot6d: torch.Tensor) -> torch.Tensor:
     """(N, 6*J) -> (N, 3*J); drop-in for acr.utils.rot6D_to_angular."""

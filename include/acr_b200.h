@@ -87,6 +87,17 @@ int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, con
 int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max, float focal_length,
                        float img_size, float* cam_trans, void* stream);
 
+/* Temporal OneEuro smoothing of poses / betas between parse and MANO, in place, on the device
+ * (SURVEY.md 8f-3).  Replaces OneEuroFilter / LowPassFilter (acr/utils.py:1485-1527), smooth_results
+ * (:1478-1482), smooth_global_rot_matrix (:1466-1470) and the per-frame host loop of acr/main.py:69-83.
+ * `state`: device buffer of acr_b200_one_euro_state_floats() floats, zero-initialised = "no history";
+ * one filter bank per hand type (0 left, 1 right), like the reference's filter_dict -- i.e. for streaming
+ * one frame at a time (the reference asserts exactly two rows).  Rows with detection_flag == 0 are skipped.
+ * poses (n,48) and betas (n,10) are updated in place.                                              */
+size_t acr_b200_one_euro_state_floats(void);
+int acr_b200_one_euro_smooth(float* poses, float* betas, const int32_t* hand_type, const float* detection_flag,
+                             const int32_t* n_dev, int n_max, float* state, float smooth_coeff, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Rotations
  * ---------------------------------------------------------------------------------------- */

@@ -104,3 +104,38 @@ def batch_rodrigues(aa):
     return np.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
                      2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
                      2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], -1).astype(F)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Temporal smoothing (acr/utils.py:1466-1527, acr/main.py:69-83)
+# ---------------------------------------------------------------------------------------------------------
+class OneEuroBank:
+    """numpy restatement of create_OneEuroFilter + smooth_results for one hand type: OneEuroFilter(c,0.7) on the
+    hand pose, OneEuroFilter(0.6,0.7) on betas, OneEuroFilter(c,0.7) on the root rotation MATRIX (float32)."""
+
+    def __init__(self, smooth_coeff=4.0, freq=30.0):
+        self.c, self.freq = F(smooth_coeff), F(freq)
+        self.prev = None       # (raw, filtered, filtered_dx) of the 64-vector [pose45 | betas10 | R9]
+
+    def _alpha(self, cutoff):
+        te = F(1.0) / self.freq
+        tau = F(1.0) / (F(2 * np.pi) * cutoff)
+        return (F(1.0) / (F(1.0) + tau / te)).astype(F)
+
+    def process(self, pose48, betas10):
+        pose48, betas10 = np.asarray(pose48, F), np.asarray(betas10, F)
+        R = batch_rodrigues(pose48[None, :3])[0]
+        x = np.concatenate([pose48[3:], betas10, R]).astype(F)
+        minc = np.concatenate([np.full(45, self.c, F), np.full(10, 0.6, F), np.full(9, self.c, F)])
+        if self.prev is None:
+            xh, edx = x.copy(), np.zeros_like(x)
+        else:
+            raw, filt, fdx = self.prev
+            dx = (x - raw) * self.freq
+            ad = self._alpha(F(1.0))
+            edx = (ad * dx + (F(1.0) - ad) * fdx).astype(F)
+            a = self._alpha(minc + F(0.7) * np.abs(edx))
+            xh = (a * x + (F(1.0) - a) * filt).astype(F)
+        self.prev = (x, xh, edx)
+        root = rotmat_to_angle_axis(xh[55:].reshape(1, 3, 3))[0]
+        return np.concatenate([root, xh[:45]]).astype(F), xh[45:55].astype(F)

@@ -95,6 +95,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "rot_golden.npz"), rot6d=r6.reshape(4, 96), aa=aa,
                         aa_in=aa_in, rodrigues=rod)
 
+    # ------------------------------------------------------- temporal smoothing (acr/utils.py:1466-1527)
+    filt = {0: ref_utils.create_OneEuroFilter(4.0), 1: ref_utils.create_OneEuroFilter(4.0)}
+    T = 8
+    rng_s = np.random.default_rng(21)       # own stream: the other fixtures keep their inputs
+    seq_p = (rng_s.standard_normal((T, 2, 48)) * 0.3).astype(np.float32) + (rng_s.standard_normal((1, 2, 48)) * 0.5).astype(np.float32)
+    seq_b = (rng_s.standard_normal((T, 2, 10)) * 0.2).astype(np.float32)
+    det = np.ones((T, 2), np.float32)
+    det[3, 0] = 0                       # left hand lost in frame 3: not filtered, history untouched
+    out_p, out_b = seq_p.copy(), seq_b.copy()
+    for t in range(T):
+        for sid in range(2):
+            if det[t, sid] == 0:
+                continue
+            pp, bb = ref_utils.smooth_results(filt[sid], torch.from_numpy(seq_p[t, sid].copy()), torch.from_numpy(seq_b[t, sid].copy()))
+            out_p[t, sid], out_b[t, sid] = pp.numpy(), bb.numpy()
+    np.savez_compressed(os.path.join(HERE, "smooth_golden.npz"), poses=seq_p, betas=seq_b, det=det, out_poses=out_p, out_betas=out_b)
+
     # ----------------------------------------------------------------------- MANO
     mw = MANOWrapper().eval()
     n = 10

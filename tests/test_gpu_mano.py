@@ -117,3 +117,17 @@ def test_mano_batch512_mixed_sides_and_edges(wrapper, assets):
     assert rel_err(out["pj2d_org"].cpu().numpy()[:N - 5], ref["pj2d_org"][:N - 5]) < TOL
     # size-independent property: rigid root rotation commutes with the forward pass (centred output)
     torch.cuda.synchronize()
+
+
+def test_one_euro_smoothing_device():
+    """acr_b200_one_euro_smooth vs the reference's filter objects (smooth_golden.npz), frame by frame."""
+    from acr_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "smooth_golden.npz"))
+    st = ops.OneEuroState("cuda")
+    ht = torch.tensor([0, 1], dtype=torch.int32).cuda()
+    for t in range(g["poses"].shape[0]):
+        poses = torch.from_numpy(g["poses"][t].copy()).cuda()
+        betas = torch.from_numpy(g["betas"][t].copy()).cuda()
+        ops.one_euro_smooth(poses, betas, st, 4.0, hand_type=ht, detection_flag=torch.from_numpy(g["det"][t].copy()).cuda())
+        assert np.abs(poses.cpu().numpy() - g["out_poses"][t]).max() < 5e-5, t
+        assert np.abs(betas.cpu().numpy() - g["out_betas"][t]).max() < 1e-6, t

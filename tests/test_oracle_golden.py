@@ -115,3 +115,17 @@ def test_network_forward(golden_dir):
     assert _rel(m["verts"], g["verts"]) < 5e-4
     assert _rel(m["j3d"], g["j3d"]) < 5e-4
     assert _rel(m["pj2d_org"], g["pj2d_org"]) < 5e-4
+
+
+def test_one_euro_smoothing(golden_dir):
+    """OneEuro filter banks (acr/utils.py:1466-1527) driven like acr/main.py:69-83, incl. a frame where one
+    hand is not detected (no filtering, history untouched)."""
+    g = np.load(os.path.join(golden_dir, "smooth_golden.npz"))
+    banks = [rotation_ref.OneEuroBank(4.0), rotation_ref.OneEuroBank(4.0)]
+    for t in range(g["poses"].shape[0]):
+        for sid in range(2):
+            if g["det"][t, sid] == 0:
+                continue
+            p, b = banks[sid].process(g["poses"][t, sid], g["betas"][t, sid])
+            assert np.abs(p - g["out_poses"][t, sid]).max() < 2e-5, (t, sid)
+            assert np.abs(b - g["out_betas"][t, sid]).max() < 1e-6, (t, sid)
