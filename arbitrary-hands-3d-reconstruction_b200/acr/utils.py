@@ -81,3 +81,24 @@ def load_model(path, model, prefix='module.', drop_prefix='', optimizer=None, **
     if hasattr(model, 'invalidate_engine'):
         model.invalidate_engine()
     return model
+
+
+def reorganize_results(outputs, img_paths, reorganize_idx):
+    """Host-side packaging of one batch into ``{img_path: [per-hand dict, ...]}`` with fp16 numpy payloads,
+    detected hands only (acr/utils.py:1226-1271).  One D2H per tensor, like the reference."""
+    import numpy as np
+    to_np = lambda t, dt=np.float16: t.detach().cpu().numpy().astype(dt)
+    detected = outputs['detection_flag_cache'].detach().cpu().numpy().astype(np.bool_)
+    pd = outputs['params_dict']
+    fields = dict(cam=to_np(pd['cam']), cam_trans=to_np(outputs['cam_trans']), poses=to_np(pd['poses']),
+                  betas=to_np(pd['betas']), j3d=to_np(outputs['j3d']), verts=to_np(outputs['verts']),
+                  pj2d=to_np(outputs['pj2d']), pj2d_org=to_np(outputs['pj2d_org']),
+                  hand_type=to_np(outputs['output_hand_type'], np.int32))
+    fields = {k: v[detected] for k, v in fields.items()}
+    reorganize_idx = np.asarray(reorganize_idx)
+    results = {}
+    for vid in np.unique(reorganize_idx):
+        rows = np.where(reorganize_idx == vid)[0]
+        results[img_paths[rows[0]]] = [dict({k: v[r] for k, v in fields.items()}, detection_flag_cache=detected[r])
+                                       for r in rows]
+    return results

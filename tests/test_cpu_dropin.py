@@ -100,3 +100,22 @@ def test_config_shim():
         assert args() is cur and args().model_precision == "fp16"
     ConfigContext(parse_args([]))
     assert args().model_precision == "bf16"
+
+
+def test_reorganize_results_packaging():
+    """acr.utils.reorganize_results (acr/utils.py:1226-1271): per-image list of per-hand dicts, fp16 payloads."""
+    from acr.utils import reorganize_results
+    n = 4
+    g = torch.Generator().manual_seed(0)
+    out = {"detection_flag_cache": torch.ones(n, dtype=torch.bool), "cam_trans": torch.randn(n, 3, generator=g),
+           "j3d": torch.randn(n, 21, 3, generator=g), "verts": torch.randn(n, 778, 3, generator=g),
+           "pj2d": torch.randn(n, 21, 2, generator=g), "pj2d_org": torch.randn(n, 21, 2, generator=g),
+           "output_hand_type": torch.tensor([0, 0, 1, 1], dtype=torch.int32),
+           "params_dict": {"cam": torch.randn(n, 3, generator=g), "poses": torch.randn(n, 48, generator=g),
+                           "betas": torch.randn(n, 10, generator=g)}}
+    idx = np.array([0, 1, 0, 1])
+    res = reorganize_results(out, ["a.jpg", "b.jpg", "a.jpg", "b.jpg"], idx)
+    assert set(res) == {"a.jpg", "b.jpg"} and len(res["a.jpg"]) == 2
+    assert res["a.jpg"][0]["hand_type"] == 0 and res["a.jpg"][1]["hand_type"] == 1
+    assert res["b.jpg"][1]["verts"].dtype == np.float16 and res["b.jpg"][1]["verts"].shape == (778, 3)
+    assert np.array_equal(res["b.jpg"][0]["poses"], out["params_dict"]["poses"][1].numpy().astype(np.float16))
