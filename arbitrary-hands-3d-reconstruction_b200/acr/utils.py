@@ -102,3 +102,21 @@ def reorganize_results(outputs, img_paths, reorganize_idx):
         results[img_paths[rows[0]]] = [dict({k: v[r] for k, v in fields.items()}, detection_flag_cache=detected[r])
                                        for r in rows]
     return results
+
+
+def img_preprocess(image, imgpath=None, input_size=512, single_img_input=False, bbox=None):
+    """Drop-in for acr/utils.py:1315-1337 on the device: ``image`` is a BGR frame (numpy HxWx3 uint8, or a CUDA
+    uint8 tensor HxWx3 / NxHxWx3); returns the reference's dict with ``image`` (uint8 RGB, white-padded to a
+    square and bicubic-resized to input_size) as a CUDA tensor and the 10-element ``offsets``."""
+    from acr_b200.preprocess import preprocess_frames
+    import numpy as np
+    t = torch.from_numpy(np.ascontiguousarray(image)) if isinstance(image, np.ndarray) else image
+    t = t.cuda(non_blocking=True)
+    batched = t.dim() == 4
+    out, offsets = preprocess_frames(t if batched else t[None], input_size)
+    if not batched and not single_img_input:
+        out, offsets = out[0], offsets[0]
+    input_data = {'image': out, 'offsets': offsets, 'data_set': 'internet'}
+    if imgpath is not None:
+        input_data.update({'imgpath': imgpath, 'name': os.path.basename(imgpath)})
+    return input_data

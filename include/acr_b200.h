@@ -87,6 +87,16 @@ int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, con
 int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max, float focal_length,
                        float img_size, float* cam_trans, void* stream);
 
+/* Frame pre-processing on the device: n BGR frames (n,H,W,3) -> RGB, white (255) pad to a
+ * `side` x `side` square (pad_t rows above, pad_l columns left), bicubic resize to out_size x out_size.
+ * Replaces img_preprocess / process_image_ori / image_pad_white_bg + cv2.resize(INTER_CUBIC)
+ * (acr/utils.py:1303-1337).  Integer arithmetic of OpenCV's generic 8-bit cubic path (11-bit coefficients,
+ * replicate border, (sum + 2^21) >> 22); the (out_size,4) int16 coefficient and (out_size) int32 offset
+ * tables come from acr_b200/preprocess.py::cubic_tables (host, float32 like OpenCV).                   */
+int acr_b200_preprocess(const uint8_t* frames_bgr, int n, int H, int W, const int16_t* coef_x,
+                        const int32_t* ofs_x, const int16_t* coef_y, const int32_t* ofs_y, int side, int pad_t,
+                        int pad_l, int out_size, uint8_t* out_rgb, void* stream);
+
 /* Temporal OneEuro smoothing of poses / betas between parse and MANO, in place, on the device
  * (SURVEY.md 8f-3).  Replaces OneEuroFilter / LowPassFilter (acr/utils.py:1485-1527), smooth_results
  * (:1478-1482), smooth_global_rot_matrix (:1466-1470) and the per-frame host loop of acr/main.py:69-83.
