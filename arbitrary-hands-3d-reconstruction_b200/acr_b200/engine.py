@@ -90,8 +90,9 @@ class Engine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, device, act_dtype=torch.bfloat16,
                  input_size: int = 512, debug_ref_conv: bool = False, reuse_memory: bool = True,
-                 dry_run: bool = False, keep_extra=()):
+                 dry_run: bool = False, keep_extra=(), stem_on_tensor_cores: bool = True):
         self.keep_extra = tuple(keep_extra)   # extra tensor names kept alive after the run (tests)
+        self.stem_on_tensor_cores = stem_on_tensor_cores
         self.dry_run = dry_run      # layout only (arena size, op list); used by CPU tests
         if not dry_run and not torch.cuda.is_available():
             raise L.AcrB200Error("Engine needs a CUDA device; there is no CPU fallback on the product path")
@@ -193,6 +194,13 @@ class Engine:
                 recs.append(dict(kind=L.OP_CONV_REF if self.debug_ref_conv else L.OP_CONV, out=op.out,
                                  ins=[op.ins[1]], aux=[bias_img[s]],
                                  attrs=dict(k=1, s=1, relu=False, residual=False, pow11=False, fold_side=s)))
+            elif op.kind == "stem" and self.stem_on_tensor_cores:
+                # conv1 + bn1 + relu as im2col (27 normalised taps -> 32 channels) + a 1x1 tcgen05 conv
+                cols = Tensor("stem_im2col", 32, op.out.H, op.out.W, "act")
+                spec.tensors[cols.name] = cols
+                recs.append(dict(kind=L.OP_IM2COL_STEM, out=cols, ins=[op.ins[0]]))
+                recs.append(dict(kind=L.OP_CONV_REF if self.debug_ref_conv else L.OP_CONV, out=op.out, ins=[cols],
+                                 attrs=dict(k=1, s=1, relu=True, residual=False, pow11=False, stem=op.attrs)))
             elif op.kind == "coordcat":
                 recs.append(dict(kind=L.OP_COORD, out=op.out, ins=[op.ins[0]]))
             else:
@@ -278,7 +286,17 @@ class Engine:
                 # ~620 clk whatever its size, so fewer, fatter boxes win (tools/tma_bench.cu)
                 o.cin_pad = 64 if 32 < x.C <= 64 else _rup(x.C, 16)
                 o.cout_pad = _rup(r["out"].C, 16)
-                if "fold_side" in a:
+                if "stem" in a:
+                    # weights (64,3,3,3) OIHW -> (64, 32, 1, 1) with input channel (ky*3+kx)*3+ci; BN folded by pack_conv
+                    w = f32(a["stem"]["w"] + ".weight")
+                    w1 = np.zeros((64, 32, 1, 1), np.float32)
+                    w1[:, :27, 0, 0] = w.transpose(0, 2, 3, 1).reshape(64, 27)
+                    sd_stem = {"stem.weight": w1}
+                    for nme in ("weight", "bias", "running_mean", "running_var"):
+                        sd_stem[f"stembn.{nme}"] = f32(f"{a['stem']['bn']}.{nme}")
+                    o.cin_pad, o.cout_pad = 32, 64
+                    o.w_offset[0], o.w_offset[1] = self._pack_conv(sd_stem, blob, "stem", "stembn", False, 32, 64)
+                elif "fold_side" in a:
                     # out = W[:, :109].pm + W[:, 109:112].pm[:3] + (b + W[:, 112:].pare),  pm = [cam3 | params106]
                     # (acr/model.py:158-164); input channel order of the 128-wide tensor: params at 0..105, cam at 112..114
                     W = f32(f"contact_layers.{4 if a['fold_side'] == 'l' else 5}.weight").reshape(109, 218)

@@ -79,6 +79,50 @@ int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, cons
   return ACR_B200_OK;
 }
 
+// ------------------------------------------------------------------------------ im2col stem
+// The stem conv (acr/model.py:832-835) on the tensor cores: this kernel only gathers the 27 normalised taps
+// of every stride-2 output pixel into a 32-channel 16-bit tensor (channel (ky*3+kx)*3+ci, 0 for taps in the
+// conv padding and for channels 27..31); the 27->64 contraction + BN + ReLU is then a 1x1 conv_tc launch.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const uint8_t* __restrict__ img, T* __restrict__ out,
+                                                          int H, int W, int out_stride, long long total) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total) return;
+  const int Ho = H / 2, Wo = W / 2;
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
+  const long long b = pix / ((long long)Wo * Ho);
+  float v[32];
+#pragma unroll
+  for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 + ky - 1;
+    const bool yok = iy >= 0 && iy < H;
+    const uint8_t* row = img + ((b * H + (yok ? iy : 0)) * (long long)W) * 3;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 + kx - 1;
+      const bool ok = yok && ix >= 0 && ix < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        v[(ky * 3 + kx) * 3 + ci] = ok ? (float)row[ix * 3 + ci] / 255.f * 2.0f - 1.0f : 0.f;
+    }
+  }
+  T* o = out + pix * out_stride;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(o + c * 8) = pack8<T>(v + c * 8);
+}
+
+int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st) {
+  ACR_CHECK_ARG(out.C == 32 && out.H * 2 == img.H && out.W * 2 == img.W && img.dtype == ACR_DT_U8 && out.pix_stride >= 32,
+                "im2col_stem: shape mismatch");
+  const long long total = (long long)batch * out.H * out.W;
+  ACR_DISPATCH_ACT(act_dtype, im2col_stem_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                                  (const uint8_t*)img.ptr, (T*)out.ptr, img.H, img.W, out.pix_stride, total));
+  ACR_CHECK_LAUNCH();
+  return ACR_B200_OK;
+}
+
 // ---------------------------------------------------------------------------- reference conv
 // Same contract as the tcgen05 conv (ConvArgs): NHWC, weights [cout_pad][k*k][cin_pad], fp32
 // accumulate, epilogue = +bias (+residual) (ReLU), 16-bit or fp32 NHWC output.

@@ -25,6 +25,7 @@ struct FuseArgs {
 // every launcher returns an ACR_B200_* status and performs exactly ONE kernel launch
 int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, const float* bias, int batch,
                 int act_dtype, cudaStream_t st);
+int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st);
 int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st);
 int launch_fuse(const FuseArgs& a, int act_dtype, cudaStream_t st);
 int launch_bilinear2x(const TensorRef& in, const TensorRef& out, int batch, int act_dtype, cudaStream_t st);

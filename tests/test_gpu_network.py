@@ -63,6 +63,23 @@ def _cmp(out, ref, tol):
     return worst
 
 
+@pytest.mark.parametrize("tc_stem", [True, False])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
+def test_stem_vs_oracle(sd, image, tc_stem, dtype, tol):
+    """conv1 + bn1 + ReLU on uint8 frames (acr/model.py:831-835): the im2col + tcgen05 1x1 form and the
+    direct CUDA-core form against the oracle's fp32 conv (error = 16-bit rounding of taps/weights/output)."""
+    from acr_b200.engine import Engine
+    from oracle import net_ref
+    eng = Engine(sd, image.shape[0], "cuda", dtype, keep_extra=("t1_stem1",), stem_on_tensor_cores=tc_stem)
+    eng.run(image.cuda())
+    torch.cuda.synchronize()
+    got = eng.view("t1_stem1")[..., :64].permute(0, 3, 1, 2).float().cpu()
+    net = net_ref._Net(sd)
+    x = (image.float().permute(0, 3, 1, 2) / 255.0) * 2.0 - 1.0
+    ref = net.cbr(x, "backbone.conv1", "backbone.bn1", stride=2)
+    assert rel_err(got.numpy(), ref.numpy()) < tol
+
+
 def test_plan_fp16_refconv_vs_oracle(sd, image, oracle_out):
     """Everything except the tensor-core conv (stem, fuse, bilinear, pooling, part head, plan wiring)."""
     _, out = _engine_maps(sd, image, ref_conv=True, dtype=torch.float16)
