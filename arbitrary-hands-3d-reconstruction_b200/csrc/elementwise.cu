@@ -85,12 +85,12 @@ int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, cons
 // conv padding and for channels 27..31); the 27->64 contraction + BN + ReLU is then a 1x1 conv_tc launch.
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const uint8_t* __restrict__ img, T* __restrict__ out,
-                                                          int H, int W, int out_stride, long long total) {
-  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (pix >= total) return;
+                                                          int H, int W, int out_stride) {
+  // grid = (ceil(Wo/256), Ho, B): no integer divisions on the address path
   const int Ho = H / 2, Wo = W / 2;
-  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
-  const long long b = pix / ((long long)Wo * Ho);
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
+  if (ox >= Wo) return;
+  const size_t b = blockIdx.z;
   float v[32];
 #pragma unroll
   for (int i = 27; i < 32; ++i) v[i] = 0.f;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const uint8_t* __restr
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy * 2 + ky - 1;
     const bool yok = iy >= 0 && iy < H;
-    const uint8_t* row = img + ((b * H + (yok ? iy : 0)) * (long long)W) * 3;
+    const uint8_t* row = img + ((b * H + (yok ? iy : 0)) * (size_t)W) * 3;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * 2 + kx - 1;
@@ -108,17 +108,17 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const uint8_t* __restr
         v[(ky * 3 + kx) * 3 + ci] = ok ? (float)row[ix * 3 + ci] / 255.f * 2.0f - 1.0f : 0.f;
     }
   }
-  T* o = out + pix * out_stride;
+  T* o = out + ((b * Ho + oy) * (size_t)Wo + ox) * out_stride;
 #pragma unroll
   for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(o + c * 8) = pack8<T>(v + c * 8);
 }
 
 int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st) {
-  ACR_CHECK_ARG(out.C == 32 && out.H * 2 == img.H && out.W * 2 == img.W && img.dtype == ACR_DT_U8 && out.pix_stride >= 32,
-                "im2col_stem: shape mismatch");
-  const long long total = (long long)batch * out.H * out.W;
-  ACR_DISPATCH_ACT(act_dtype, im2col_stem_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                                  (const uint8_t*)img.ptr, (T*)out.ptr, img.H, img.W, out.pix_stride, total));
+  ACR_CHECK_ARG(out.C == 32 && out.H * 2 == img.H && out.W * 2 == img.W && img.dtype == ACR_DT_U8 && out.pix_stride >= 32 &&
+                    out.pix_stride % 8 == 0 && out.H <= 65535 && batch <= 65535, "im2col_stem: shape mismatch");
+  const dim3 grid((unsigned)((out.W + 255) / 256), (unsigned)out.H, (unsigned)batch);
+  ACR_DISPATCH_ACT(act_dtype, im2col_stem_kernel<T><<<grid, 256, 0, st>>>((const uint8_t*)img.ptr, (T*)out.ptr, img.H, img.W,
+                                                                           out.pix_stride));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
@@ -201,22 +201,22 @@ int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st) {
 // HighResolutionModule.forward :677-684: y = relu(sum_j f_ij(x_j)), nearest upsample for j > i.
 // thread = (pixel, 8 channels); fp32 sum in the reference's order, one rounding.
 template <typename T>
-__global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a, long long total) {
-  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (gid >= total) return;
-  const int ngrp = a.out.C / 8;
-  const int cg = (int)(gid % ngrp);
-  const long long pix = gid / ngrp;
-  const int W = a.out.W, H = a.out.H;
-  const int x = (int)(pix % W), y = (int)((pix / W) % H);
-  const size_t b = (size_t)(pix / ((long long)W * H));
+__global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
+  // grid = (ceil(W * C/8 / 256), H, B): one 32-bit division per thread, none on 64-bit values
+  const unsigned ngrp = a.out.C / 8;
+  const unsigned tid = blockIdx.x * 256 + threadIdx.x;
+  const unsigned x = tid / ngrp, cg = tid - x * ngrp;
+  if (x >= (unsigned)a.out.W) return;
+  const unsigned y = blockIdx.y;
+  const size_t b = blockIdx.z;
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 4
   for (int i = 0; i < a.n_in; ++i) {
     const TensorRef& t = a.in[i];
-    const int sx = x >> a.shift[i], sy = y >> a.shift[i];
-    const T* p = (const T*)t.ptr + (b * t.H * t.W + (size_t)sy * t.W + sx) * t.pix_stride + cg * 8;
+    const unsigned sx = x >> a.shift[i], sy = y >> a.shift[i];
+    const T* p = (const T*)t.ptr + ((b * t.H + sy) * (size_t)t.W + sx) * t.pix_stride + cg * 8;
     float v[8];
     unpack8<T>(*reinterpret_cast<const uint4*>(p), v);
 #pragma unroll
@@ -226,16 +226,19 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a, long long total) 
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
   }
-  T* o = (T*)a.out.ptr + (size_t)pix * a.out.pix_stride + cg * 8;
+  T* o = (T*)a.out.ptr + ((b * a.out.H + y) * (size_t)a.out.W + x) * a.out.pix_stride + cg * 8;
   *reinterpret_cast<uint4*>(o) = pack8<T>(acc);
 }
 
+static inline dim3 row_grid(const TensorRef& out, int batch) {
+  return dim3((unsigned)((out.W * (out.C / 8) + 255) / 256), (unsigned)out.H, (unsigned)batch);
+}
+
 int launch_fuse(const FuseArgs& a, int act_dtype, cudaStream_t st) {
-  ACR_CHECK_ARG(a.n_in >= 1 && a.n_in <= 4 && a.out.C % 8 == 0, "fuse: bad arguments");
+  ACR_CHECK_ARG(a.n_in >= 1 && a.n_in <= 4 && a.out.C % 8 == 0 && a.out.H <= 65535 && a.batch <= 65535, "fuse: bad arguments");
   for (int i = 0; i < a.n_in; ++i)
     ACR_CHECK_ARG(a.in[i].C == a.out.C && (a.in[i].H << a.shift[i]) == a.out.H, "fuse: term %d shape mismatch", i);
-  const long long total = (long long)a.batch * a.out.H * a.out.W * (a.out.C / 8);
-  ACR_DISPATCH_ACT(act_dtype, fuse_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total));
+  ACR_DISPATCH_ACT(act_dtype, fuse_kernel<T><<<row_grid(a.out, a.batch), 256, 0, st>>>(a));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
@@ -243,14 +246,13 @@ int launch_fuse(const FuseArgs& a, int act_dtype, cudaStream_t st) {
 // ------------------------------------------------------------------------------- bilinear x2
 // Up.forward :432  F.interpolate(scale 2, bilinear, align_corners=True)
 template <typename T>
-__global__ void __launch_bounds__(256) bilinear2x_kernel(TensorRef in, TensorRef out, long long total) {
-  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (gid >= total) return;
-  const int ngrp = out.C / 8;
-  const int cg = (int)(gid % ngrp);
-  const long long pix = gid / ngrp;
-  const int x = (int)(pix % out.W), y = (int)((pix / out.W) % out.H);
-  const size_t b = (size_t)(pix / ((long long)out.W * out.H));
+__global__ void __launch_bounds__(256) bilinear2x_kernel(TensorRef in, TensorRef out) {
+  const unsigned ngrp = out.C / 8;
+  const unsigned tid = blockIdx.x * 256 + threadIdx.x;
+  const unsigned xu = tid / ngrp, cg = tid - xu * ngrp;
+  if (xu >= (unsigned)out.W) return;
+  const int x = (int)xu, y = (int)blockIdx.y;
+  const size_t b = blockIdx.z;
   const float sy = (float)(in.H - 1) / (float)(out.H - 1), sx = (float)(in.W - 1) / (float)(out.W - 1);
   const float fy = sy * y, fx = sx * x;
   const int y0 = (int)fy, x0 = (int)fx;
@@ -265,124 +267,237 @@ __global__ void __launch_bounds__(256) bilinear2x_kernel(TensorRef in, TensorRef
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     o[c] = (1.f - ly) * ((1.f - lx) * v00[c] + lx * v01[c]) + ly * ((1.f - lx) * v10[c] + lx * v11[c]);
-  *reinterpret_cast<uint4*>((T*)out.ptr + (size_t)pix * out.pix_stride + cg * 8) = pack8<T>(o);
+  *reinterpret_cast<uint4*>((T*)out.ptr + ((b * out.H + y) * (size_t)out.W + x) * out.pix_stride + cg * 8) = pack8<T>(o);
 }
 
 int launch_bilinear2x(const TensorRef& in, const TensorRef& out, int batch, int act_dtype, cudaStream_t st) {
-  ACR_CHECK_ARG(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && in.C % 8 == 0, "bilinear2x: shapes");
-  const long long total = (long long)batch * out.H * out.W * (out.C / 8);
-  ACR_DISPATCH_ACT(act_dtype, bilinear2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, total));
+  ACR_CHECK_ARG(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && in.C % 8 == 0 && out.H <= 65535 && batch <= 65535,
+                "bilinear2x: shapes");
+  ACR_DISPATCH_ACT(act_dtype, bilinear2x_kernel<T><<<row_grid(out, batch), 256, 0, st>>>(in, out));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------ coord
 // get_coord_maps :340-369 + the cat at :52 -- channel c_off = x in [-1,1], c_off+1 = y, rest of the
-// 16-channel pad group zero.  thread = pixel.
+// pad group zero.  thread = pixel, the 8-channel groups leave as 16-byte stores (whole sectors).
 template <typename T>
-__global__ void __launch_bounds__(256) coord_kernel(TensorRef out, int c_off, int npad, long long total) {
-  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (pix >= total) return;
-  const int x = (int)(pix % out.W), y = (int)((pix / out.W) % out.H);
-  T* o = (T*)out.ptr + (size_t)pix * out.pix_stride + c_off;
-  o[0] = from_f32<T>((float)x / (float)(out.W - 1) * 2.f - 1.f);
-  o[1] = from_f32<T>((float)y / (float)(out.H - 1) * 2.f - 1.f);
-  for (int c = 2; c < npad; ++c) o[c] = from_f32<T>(0.f);
+__global__ void __launch_bounds__(256) coord_kernel(TensorRef out, int c_off, int npad) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= out.W) return;
+  const size_t b = blockIdx.z;
+  T* o = (T*)out.ptr + ((b * out.H + y) * (size_t)out.W + x) * out.pix_stride + c_off;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = 0.f;
+  v[0] = (float)x / (float)(out.W - 1) * 2.f - 1.f;
+  v[1] = (float)y / (float)(out.H - 1) * 2.f - 1.f;
+  *reinterpret_cast<uint4*>(o) = pack8<T>(v);
+  v[0] = v[1] = 0.f;
+  for (int c = 8; c < npad; c += 8) *reinterpret_cast<uint4*>(o + c) = pack8<T>(v);
 }
 
 int launch_coord(const TensorRef& out, int c_off, int batch, int act_dtype, cudaStream_t st) {
   const int npad = out.pix_stride - c_off;
-  ACR_CHECK_ARG(npad >= 2, "coord: no room for the coord channels");
-  const long long total = (long long)batch * out.H * out.W;
-  ACR_DISPATCH_ACT(act_dtype, coord_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, c_off, npad, total));
+  ACR_CHECK_ARG(npad >= 8 && npad % 8 == 0 && c_off % 8 == 0 && out.pix_stride % 8 == 0 && out.H <= 65535 && batch <= 65535,
+                "coord: the coord channels need an aligned 8-channel group");
+  const dim3 grid((unsigned)((out.W + 255) / 256), (unsigned)out.H, (unsigned)batch);
+  ACR_DISPATCH_ACT(act_dtype, coord_kernel<T><<<grid, 256, 0, st>>>(out, c_off, npad));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
 
 // ------------------------------------------------------------------------- attention pooling
 // Hadamard_product :103-113 on the contact features with part_attention = nearest-1/2 of the
-// segmentation logits minus the background channel (:126-128).  Split-softmax: CTA (b, chunk)
-// handles 1024 pixels, emits un-normalised sums acc[c][j] = sum_p exp(l_jp - m_j) f_pc together
-// with (m_j, s_j); launch_parthead merges the 16 chunks.  thread = feature channel.
+// segmentation logits minus the background channel (:126-128).  Split-softmax: CTA (b, chunk) handles
+// HW/POOL_CHUNKS pixels and emits the un-normalised sums acc[c][j] = sum_p exp(l_jp - m_j) f_pc together
+// with (m_j, s_j); launch_parthead merges the chunks.
+//
+// The contraction over pixels is a [32 parts] x [256 channels] x [K = pixels] GEMM per image: warp-level
+// tensor-core MMAs (m16n8k16, fp32 accumulate) keep the kernel on its HBM roofline (one streaming read of
+// the feature map); the weights w = exp(l - m) are rounded to the storage type T once and s_j sums the
+// ROUNDED values, so the normalised weights still sum to one.
+constexpr int POOL_HALF = 512;                // pixels whose softmax weights are resident in shared memory
+constexpr int POOL_W_STRIDE = POOL_HALF + 8;  // elements; +16 B keeps ldmatrix rows on distinct banks
+constexpr int POOL_F_STRIDE = 40;             // elements; 32 channels + 16 B pad
+constexpr int POOL_F_TILE = 32;               // pixels per cp.async stage
+constexpr int POOL_STAGES = 3;
+// 92.5 KB: two CTAs per SM, so one CTA's weight pass overlaps the other's feature stream
+constexpr int POOL_SMEM_BYTES = 32 * POOL_W_STRIDE * 2 + 8 * POOL_STAGES * POOL_F_TILE * POOL_F_STRIDE * 2;
+
 template <typename T>
-__global__ void __launch_bounds__(256) pool_kernel(TensorRef feat, TensorRef logits, float* __restrict__ part) {
-  __shared__ __align__(16) float s_w[32][32];   // [pixel][part]
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) pool_kernel(TensorRef feat, TensorRef logits, float* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char pool_smem[];
+  T* s_w = reinterpret_cast<T*>(pool_smem);                                   // [32 parts][POOL_W_STRIDE]
+  T* s_f = s_w + 32 * POOL_W_STRIDE;                                          // [8 warps][stages][tile][40]
   __shared__ float s_red[8][32];
-  __shared__ float s_m[32];
+  __shared__ float s_m[32], s_scale[32];
   const int b = blockIdx.x, chunk = blockIdx.y, t = threadIdx.x;
   const int HW = feat.H * feat.W, per = HW / POOL_CHUNKS, p0 = chunk * per;
   const T* lg = (const T*)logits.ptr + (size_t)b * logits.img_stride();
   const T* ft = (const T*)feat.ptr + (size_t)b * feat.img_stride();
-  const int j = t & 31, sub = t >> 5;  // this thread's part channel / pixel sub-lane
-  auto logit = [&](int p) -> float {
-    const int y = p / feat.W, x = p % feat.W;
-    return to_f32<T>(lg[((size_t)(2 * y) * logits.W + 2 * x) * logits.pix_stride + 1 + j]);
+  const int j = t & 31, warp = t >> 5, lane = j;
+  if (t < 32) s_m[t] = -INFINITY;
+
+  // this warp's feature stream: channels [32 warp, 32 warp + 32), POOL_F_TILE pixels per stage
+  const int ntiles = per / POOL_F_TILE, tiles_per_half = POOL_HALF / POOL_F_TILE;
+  T* my_f = s_f + (size_t)warp * POOL_STAGES * POOL_F_TILE * POOL_F_STRIDE;
+  auto issue = [&](int tile) {
+    if (tile < ntiles) {
+      T* dst = my_f + (size_t)(tile % POOL_STAGES) * POOL_F_TILE * POOL_F_STRIDE;
+      const T* src = ft + (size_t)(p0 + tile * POOL_F_TILE) * feat.pix_stride + warp * 32;
+#pragma unroll
+      for (int i = 0; i < POOL_F_TILE / 8; ++i) {
+        const int id = i * 32 + lane, row = id >> 2, col = id & 3;
+        cp_async16(dst + row * POOL_F_STRIDE + col * 8, src + (size_t)row * feat.pix_stride + col * 8);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  // chunk maximum per part
-  float m = -INFINITY;
-  for (int p = p0 + sub; p < p0 + per; p += 8) m = fmaxf(m, logit(p));
-  s_red[sub][j] = m;
-  __syncthreads();
-  if (t < 32) {
-    float mm = s_red[0][t];
+  issue(0);
+  issue(1);
+
+  float acc[2][4][4];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mm = fmaxf(mm, s_red[i][t]);
-    s_m[t] = mm;
-  }
-  __syncthreads();
-  m = s_m[j];
-  float acc[32];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  float ssum = 0.f;
-  for (int q = p0; q < p0 + per; q += 32) {
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  const int frag_row = (lane & 7) + ((lane >> 3) & 1) * 8, frag_col = (lane >> 4) * 8;
+  const int g = lane >> 2, tq = lane & 3;
+  float ssum = 0.f;   // this thread's share of sum_p w[j][p], relative to the running maximum s_m[j]
+
+  for (int h = 0; h < per / POOL_HALF; ++h) {
+    if (h > 0) __syncthreads();   // every warp is done with the previous half's weights and scales
+    // ---- softmax weights of this half: raw logits -> running maximum -> exp, rounded to T, [part][pixel]
+    float mloc = -INFINITY;
+#pragma unroll 8
+    for (int p = warp; p < POOL_HALF; p += 8) {
+      const int P = p0 + h * POOL_HALF + p, y = P / feat.W, x = P % feat.W;
+      const T v = lg[((size_t)(2 * y) * logits.W + 2 * x) * logits.pix_stride + 1 + j];
+      s_w[j * POOL_W_STRIDE + p] = v;
+      mloc = fmaxf(mloc, to_f32<T>(v));
+    }
+    s_red[warp][j] = mloc;
     __syncthreads();
+    if (t < 32) {
+      float mm = s_red[0][t];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pp = sub + 8 * i;
-      const float w = expf(logit(q + pp) - m);
-      s_w[pp][j] = w;
-      ssum += w;
+      for (int i = 1; i < 8; ++i) mm = fmaxf(mm, s_red[i][t]);
+      const float m_old = s_m[t], m_new = fmaxf(m_old, mm);
+      s_scale[t] = expf(m_old - m_new);   // 0 for the first half
+      s_m[t] = m_new;
     }
     __syncthreads();
-    for (int p8 = 0; p8 < 32; p8 += 8) {
-      T fv[8];   // 8 independent loads in flight before the FMA block
+    const float m = s_m[j];
+    ssum *= s_scale[j];
+    for (int p = warp; p < POOL_HALF; p += 8) {
+      const T w = from_f32<T>(expf(to_f32<T>(s_w[j * POOL_W_STRIDE + p]) - m));
+      s_w[j * POOL_W_STRIDE + p] = w;
+      ssum += to_f32<T>(w);
+    }
+    __syncthreads();
+    if (h > 0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) fv[u] = ft[(size_t)(q + p8 + u) * feat.pix_stride + t];
+      for (int mt = 0; mt < 2; ++mt) {
+        const float f0 = s_scale[mt * 16 + g], f1 = s_scale[mt * 16 + g + 8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float f = to_f32<T>(fv[u]);
-        const float4* wr = reinterpret_cast<const float4*>(&s_w[p8 + u][0]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 w4 = wr[i];
-          acc[i * 4 + 0] = fmaf(w4.x, f, acc[i * 4 + 0]); acc[i * 4 + 1] = fmaf(w4.y, f, acc[i * 4 + 1]);
-          acc[i * 4 + 2] = fmaf(w4.z, f, acc[i * 4 + 2]); acc[i * 4 + 3] = fmaf(w4.w, f, acc[i * 4 + 3]);
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[mt][nt][0] *= f0; acc[mt][nt][1] *= f0; acc[mt][nt][2] *= f1; acc[mt][nt][3] *= f1;
         }
       }
     }
+    // ---- acc[part][channel] += w[part][pixel] * f[pixel][channel]
+    for (int lt = 0; lt < tiles_per_half; ++lt) {
+      const int tile = h * tiles_per_half + lt;
+      issue(tile + 2);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncwarp();
+      const T* sf = my_f + (size_t)(tile % POOL_STAGES) * POOL_F_TILE * POOL_F_STRIDE;
+#pragma unroll
+      for (int ks = 0; ks < POOL_F_TILE / 16; ++ks) {
+        uint32_t a[2][4], bq[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          ldsm_x4(a[mt], s_w + (size_t)(mt * 16 + frag_row) * POOL_W_STRIDE + lt * POOL_F_TILE + ks * 16 + frag_col);
+#pragma unroll
+        for (int np = 0; np < 2; ++np)
+          ldsm_x4_trans(bq[np], sf + (size_t)(ks * 16 + frag_row) * POOL_F_STRIDE + np * 16 + frag_col);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            mma16816<T>(acc[mt][nt], a[mt], bq[nt >> 1][(nt & 1) * 2], bq[nt >> 1][(nt & 1) * 2 + 1]);
+      }
+      __syncwarp();
+    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  s_red[warp][j] = ssum;
   __syncthreads();
-  s_red[sub][j] = ssum;
-  __syncthreads();
+
   float* o = part + ((size_t)b * POOL_CHUNKS + chunk) * POOL_PART_FLOATS;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(o + t * 32 + i * 4) = make_float4(acc[i * 4], acc[i * 4 + 1], acc[i * 4 + 2], acc[i * 4 + 3]);
-  if (t < 32) {
-    float s = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += s_red[i][t];
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = warp * 32 + nt * 8 + 2 * tq, jj = mt * 16 + g;
+      o[(size_t)c * 32 + jj] = acc[mt][nt][0];
+      o[(size_t)(c + 1) * 32 + jj] = acc[mt][nt][1];
+      o[(size_t)c * 32 + jj + 8] = acc[mt][nt][2];
+      o[(size_t)(c + 1) * 32 + jj + 8] = acc[mt][nt][3];
+    }
+  if (t < 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += s_red[i][t];
     o[256 * 32 + t] = s_m[t];
-    o[256 * 32 + 32 + t] = s;
+    o[256 * 32 + 32 + t] = sum;
   }
 }
 
 int launch_pool(const TensorRef& feat, const TensorRef& logits, float* part, int batch, int act_dtype,
                 cudaStream_t st) {
+  const int per = feat.H * feat.W / POOL_CHUNKS;
   ACR_CHECK_ARG(feat.C == 256 && logits.H == 2 * feat.H && logits.W == 2 * feat.W && logits.C >= 33 &&
-                    (feat.H * feat.W) % (POOL_CHUNKS * 32) == 0, "pool: shapes");
-  ACR_DISPATCH_ACT(act_dtype, pool_kernel<T><<<dim3(batch, POOL_CHUNKS), 256, 0, st>>>(feat, logits, part));
+                    (feat.H * feat.W) % POOL_CHUNKS == 0 && per % POOL_HALF == 0 &&
+                    feat.pix_stride % 8 == 0, "pool: shapes");
+  ACR_DISPATCH_ACT(act_dtype, {
+    static bool attr_set = false;
+    if (!attr_set) {
+      ACR_CHECK_CUDA(cudaFuncSetAttribute(pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES));
+      attr_set = true;
+    }
+    pool_kernel<T><<<dim3(batch, POOL_CHUNKS), 256, POOL_SMEM_BYTES, st>>>(feat, logits, part);
+  });
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }

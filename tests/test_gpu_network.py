@@ -80,6 +80,25 @@ def test_stem_vs_oracle(sd, image, tc_stem, dtype, tol):
     assert rel_err(got.numpy(), ref.numpy()) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-3), (torch.bfloat16, 4e-3)])
+def test_attention_pooling_vs_torch(sd, image, dtype, tol):
+    """Hadamard_product / part attention (acr/model.py:103-128) as the split-softmax tensor-core GEMM over
+    pixels: compared on the engine's OWN stored feature map and logits with an fp32 softmax + einsum (the
+    only difference is the one rounding of the softmax weights to the storage type)."""
+    from acr_b200.engine import Engine
+    spec = Engine(None, 1, "cpu", dry_run=True).spec
+    contact = [n for n in spec.tensors if n.endswith("_contact")][0]
+    eng = Engine(sd, image.shape[0], "cuda", dtype, keep_extra=(contact,))
+    eng.run(image.cuda())
+    torch.cuda.synchronize()
+    B = image.shape[0]
+    feat = eng.view(contact)[..., :256].float().reshape(B, -1, 256)
+    logit = eng.view("segms")[:, ::2, ::2, 1:33].float().reshape(B, -1, 32)
+    ref = torch.einsum("bpc,bpj->bcj", feat, torch.softmax(logit, dim=1))
+    got = eng.view("pooled").view(B, 256, 32)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < tol
+
+
 def test_plan_fp16_refconv_vs_oracle(sd, image, oracle_out):
     """Everything except the tensor-core conv (stem, fuse, bilinear, pooling, part head, plan wiring)."""
     _, out = _engine_maps(sd, image, ref_conv=True, dtype=torch.float16)
