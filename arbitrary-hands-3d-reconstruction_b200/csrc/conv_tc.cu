@@ -167,6 +167,8 @@ struct ConvTcParams {
   const void* res;
   void* out;
   int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
+  int vec256;   // output / residual rows are 32-byte aligned: 256-bit epilogue accesses
+  int ksteps;   // k16 steps of a chunk that hold real channels (the rest are TMA zero fill: skipped)
   int patch_mode, b_resident, SA, SB;
   uint32_t a_stage_bytes, b_block_bytes, b_region_bytes;
   int tmem_cols, acc_stride, nbuf;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t b_block16 = P.b_block_bytes >> 4, a_stage16 = P.a_stage_bytes >> 4;
       const uint32_t a_lo_base = ((a_base >> 4) & 0x3FFF) | lo_flags, b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
       const bool resident = P.b_resident != 0, patch = P.patch_mode != 0;
-      const int cchunks = P.cchunks;
+      const int cchunks = P.cchunks, ksteps = P.ksteps;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (elect_one_sync()) {
 #pragma unroll
               for (int ks = 0; ks < CK / 16; ++ks) {
+                if (ks >= ksteps) break;
                 const uint32_t acc_flag = (ks == 0) ? accum : 1u;
                 umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);                        // left 8 columns
                 umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);  // right 8 columns
@@ -365,8 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c * 16 < P.npad) {
-            rr[c][0] = *reinterpret_cast<const uint4*>(resp + c * 16);
-            rr[c][1] = *reinterpret_cast<const uint4*>(resp + c * 16 + 8);
+            if (P.vec256) ldg256(resp + c * 16, rr[c][0], rr[c][1]);
+            else {
+              rr[c][0] = *reinterpret_cast<const uint4*>(resp + c * 16);
+              rr[c][1] = *reinterpret_cast<const uint4*>(resp + c * 16 + 8);
+            }
           }
       }
       mbar_wait(tmem_full(buf), use & 1u);
@@ -382,8 +388,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             if (c < nch) {
-              rr[c][0] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16);
-              rr[c][1] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16 + 8);
+              if (P.vec256) ldg256(resp + g0 + c * 16, rr[c][0], rr[c][1]);
+              else {
+                rr[c][0] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16);
+                rr[c][1] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16 + 8);
+              }
             }
         }
         tmem_ld_wait();
@@ -421,8 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
             T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + c0;
-            reinterpret_cast<uint4*>(o)[0] = pack8<T>(f);
-            reinterpret_cast<uint4*>(o)[1] = pack8<T>(f + 8);
+            if (P.vec256) stg256(o, pack8<T>(f), pack8<T>(f + 8));
+            else {
+              reinterpret_cast<uint4*>(o)[0] = pack8<T>(f);
+              reinterpret_cast<uint4*>(o)[1] = pack8<T>(f + 8);
+            }
           }
         }
       }
@@ -524,6 +536,10 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   if (rc) { delete pl; return rc; }
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
+  p.ksteps = ck / 16;
+  p.vec256 = (a.out.dtype != ACR_DT_F32) && ((uintptr_t)a.out.ptr % 32 == 0) && (a.out.pix_stride % 16 == 0) &&
+             (!a.has_res || (((uintptr_t)a.res.ptr % 32 == 0) && (a.res.pix_stride % 16 == 0)));
+  if (p.cchunks == 1 && (int)((dim0 + 15) / 16) < p.ksteps) p.ksteps = (int)((dim0 + 15) / 16);
   p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
   p.bias_per_image = a.bias_per_image; p.pow11_ch0 = a.pow11_ch0;
   p.tiles_x = a.out.W / TILE_X; p.tiles_per_img = p.tiles_x * (a.out.H / TILE_Y);

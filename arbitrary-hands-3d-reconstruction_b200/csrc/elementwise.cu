@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const uint8_t* __restr
     }
   }
   T* o = out + ((b * Ho + oy) * (size_t)Wo + ox) * out_stride;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(o + c * 8) = pack8<T>(v + c * 8);
+  stg256(o, pack8<T>(v), pack8<T>(v + 8));
+  stg256(o + 16, pack8<T>(v + 16), pack8<T>(v + 24));
 }
 
 int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st) {
   ACR_CHECK_ARG(out.C == 32 && out.H * 2 == img.H && out.W * 2 == img.W && img.dtype == ACR_DT_U8 && out.pix_stride >= 32 &&
-                    out.pix_stride % 8 == 0 && out.H <= 65535 && batch <= 65535, "im2col_stem: shape mismatch");
+                    out.pix_stride % 16 == 0 && (uintptr_t)out.ptr % 32 == 0 && out.H <= 65535 && batch <= 65535, "im2col_stem: shape mismatch");
   const dim3 grid((unsigned)((out.W + 255) / 256), (unsigned)out.H, (unsigned)batch);
   ACR_DISPATCH_ACT(act_dtype, im2col_stem_kernel<T><<<grid, 256, 0, st>>>((const uint8_t*)img.ptr, (T*)out.ptr, img.H, img.W,
                                                                            out.pix_stride));
@@ -200,54 +200,67 @@ int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st) {
 // ------------------------------------------------------------------------------------ fuse
 // HighResolutionModule.forward :677-684: y = relu(sum_j f_ij(x_j)), nearest upsample for j > i.
 // thread = (pixel, 8 channels); fp32 sum in the reference's order, one rounding.
-template <typename T>
+template <typename T, int CPT>   // CPT = channels per thread: 16 -> 256-bit accesses (whole sectors), 8 -> 128-bit
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs a) {
-  // grid = (ceil(W * C/8 / 256), H, B): one 32-bit division per thread, none on 64-bit values
-  const unsigned ngrp = a.out.C / 8;
+  // grid = (ceil(W * C/CPT / 256), H, B): one 32-bit division per thread, none on 64-bit values
+  const unsigned ngrp = a.out.C / CPT;
   const unsigned tid = blockIdx.x * 256 + threadIdx.x;
   const unsigned x = tid / ngrp, cg = tid - x * ngrp;
   if (x >= (unsigned)a.out.W) return;
   const unsigned y = blockIdx.y;
   const size_t b = blockIdx.z;
-  float acc[8];
+  float acc[CPT];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
 #pragma unroll 4
   for (int i = 0; i < a.n_in; ++i) {
     const TensorRef& t = a.in[i];
     const unsigned sx = x >> a.shift[i], sy = y >> a.shift[i];
-    const T* p = (const T*)t.ptr + ((b * t.H + sy) * (size_t)t.W + sx) * t.pix_stride + cg * 8;
-    float v[8];
-    unpack8<T>(*reinterpret_cast<const uint4*>(p), v);
+    const T* p = (const T*)t.ptr + ((b * t.H + sy) * (size_t)t.W + sx) * t.pix_stride + cg * CPT;
+    float v[CPT];
+    if (CPT == 16) {
+      uint4 u0, u1;
+      ldg256(p, u0, u1);
+      unpack8<T>(u0, v);
+      unpack8<T>(u1, v + 8);
+    } else {
+      unpack8<T>(*reinterpret_cast<const uint4*>(p), v);
+    }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = (i == 0) ? v[c] : acc[c] + v[c];
+    for (int c = 0; c < CPT; ++c) acc[c] = (i == 0) ? v[c] : acc[c] + v[c];
   }
   if (a.relu) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    for (int c = 0; c < CPT; ++c) acc[c] = fmaxf(acc[c], 0.f);
   }
-  T* o = (T*)a.out.ptr + ((b * a.out.H + y) * (size_t)a.out.W + x) * a.out.pix_stride + cg * 8;
-  *reinterpret_cast<uint4*>(o) = pack8<T>(acc);
+  T* o = (T*)a.out.ptr + ((b * a.out.H + y) * (size_t)a.out.W + x) * a.out.pix_stride + cg * CPT;
+  if (CPT == 16) stg256(o, pack8<T>(acc), pack8<T>(acc + 8));
+  else *reinterpret_cast<uint4*>(o) = pack8<T>(acc);
 }
 
-static inline dim3 row_grid(const TensorRef& out, int batch) {
-  return dim3((unsigned)((out.W * (out.C / 8) + 255) / 256), (unsigned)out.H, (unsigned)batch);
+static inline dim3 row_grid(const TensorRef& out, int batch, int cpt) {
+  return dim3((unsigned)((out.W * (out.C / cpt) + 255) / 256), (unsigned)out.H, (unsigned)batch);
 }
+static inline bool rows32(const TensorRef& t) { return (uintptr_t)t.ptr % 32 == 0 && t.pix_stride % 16 == 0 && t.C % 16 == 0; }
 
 int launch_fuse(const FuseArgs& a, int act_dtype, cudaStream_t st) {
   ACR_CHECK_ARG(a.n_in >= 1 && a.n_in <= 4 && a.out.C % 8 == 0 && a.out.H <= 65535 && a.batch <= 65535, "fuse: bad arguments");
-  for (int i = 0; i < a.n_in; ++i)
+  bool wide = rows32(a.out);
+  for (int i = 0; i < a.n_in; ++i) {
     ACR_CHECK_ARG(a.in[i].C == a.out.C && (a.in[i].H << a.shift[i]) == a.out.H, "fuse: term %d shape mismatch", i);
-  ACR_DISPATCH_ACT(act_dtype, fuse_kernel<T><<<row_grid(a.out, a.batch), 256, 0, st>>>(a));
+    wide = wide && rows32(a.in[i]);
+  }
+  if (wide) ACR_DISPATCH_ACT(act_dtype, fuse_kernel<T, 16><<<row_grid(a.out, a.batch, 16), 256, 0, st>>>(a));
+  else ACR_DISPATCH_ACT(act_dtype, fuse_kernel<T, 8><<<row_grid(a.out, a.batch, 8), 256, 0, st>>>(a));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
 
 // ------------------------------------------------------------------------------- bilinear x2
 // Up.forward :432  F.interpolate(scale 2, bilinear, align_corners=True)
-template <typename T>
+template <typename T, int CPT>
 __global__ void __launch_bounds__(256) bilinear2x_kernel(TensorRef in, TensorRef out) {
-  const unsigned ngrp = out.C / 8;
+  const unsigned ngrp = out.C / CPT;
   const unsigned tid = blockIdx.x * 256 + threadIdx.x;
   const unsigned xu = tid / ngrp, cg = tid - xu * ngrp;
   if (xu >= (unsigned)out.W) return;
@@ -258,22 +271,33 @@ __global__ void __launch_bounds__(256) bilinear2x_kernel(TensorRef in, TensorRef
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
   const float ly = fy - y0, lx = fx - x0;
-  const T* base = (const T*)in.ptr + b * in.img_stride() + cg * 8;
-  float v00[8], v01[8], v10[8], v11[8], o[8];
-  unpack8<T>(*reinterpret_cast<const uint4*>(base + ((size_t)y0 * in.W + x0) * in.pix_stride), v00);
-  unpack8<T>(*reinterpret_cast<const uint4*>(base + ((size_t)y0 * in.W + x1) * in.pix_stride), v01);
-  unpack8<T>(*reinterpret_cast<const uint4*>(base + ((size_t)y1 * in.W + x0) * in.pix_stride), v10);
-  unpack8<T>(*reinterpret_cast<const uint4*>(base + ((size_t)y1 * in.W + x1) * in.pix_stride), v11);
+  const T* base = (const T*)in.ptr + b * in.img_stride() + cg * CPT;
+  float v00[CPT], v01[CPT], v10[CPT], v11[CPT], o[CPT];
+  auto load = [&](int yy, int xx, float* v) {
+    const T* p = base + ((size_t)yy * in.W + xx) * in.pix_stride;
+    if (CPT == 16) {
+      uint4 u0, u1;
+      ldg256(p, u0, u1);
+      unpack8<T>(u0, v);
+      unpack8<T>(u1, v + 8);
+    } else {
+      unpack8<T>(*reinterpret_cast<const uint4*>(p), v);
+    }
+  };
+  load(y0, x0, v00); load(y0, x1, v01); load(y1, x0, v10); load(y1, x1, v11);
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < CPT; ++c)
     o[c] = (1.f - ly) * ((1.f - lx) * v00[c] + lx * v01[c]) + ly * ((1.f - lx) * v10[c] + lx * v11[c]);
-  *reinterpret_cast<uint4*>((T*)out.ptr + ((b * out.H + y) * (size_t)out.W + x) * out.pix_stride + cg * 8) = pack8<T>(o);
+  T* op = (T*)out.ptr + ((b * out.H + y) * (size_t)out.W + x) * out.pix_stride + cg * CPT;
+  if (CPT == 16) stg256(op, pack8<T>(o), pack8<T>(o + 8));
+  else *reinterpret_cast<uint4*>(op) = pack8<T>(o);
 }
 
 int launch_bilinear2x(const TensorRef& in, const TensorRef& out, int batch, int act_dtype, cudaStream_t st) {
   ACR_CHECK_ARG(out.H == 2 * in.H && out.W == 2 * in.W && out.C == in.C && in.C % 8 == 0 && out.H <= 65535 && batch <= 65535,
                 "bilinear2x: shapes");
-  ACR_DISPATCH_ACT(act_dtype, bilinear2x_kernel<T><<<row_grid(out, batch), 256, 0, st>>>(in, out));
+  if (rows32(in) && rows32(out)) ACR_DISPATCH_ACT(act_dtype, bilinear2x_kernel<T, 16><<<row_grid(out, batch, 16), 256, 0, st>>>(in, out));
+  else ACR_DISPATCH_ACT(act_dtype, bilinear2x_kernel<T, 8><<<row_grid(out, batch, 8), 256, 0, st>>>(in, out));
   ACR_CHECK_LAUNCH();
   return ACR_B200_OK;
 }
