@@ -309,6 +309,7 @@ class Engine:
                 elif pair:
                     o.cin_pad = o.cout_pad = 64
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, 64, pair=True)
+                    o.shift[0] = 4      # ACR_CONV_XPAIR: side taps are 32x32 corners of the 64x64 block
                 else:
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
                     if a.get("pow11"):

@@ -167,6 +167,8 @@ struct ConvTcParams {
   const void* res;
   void* out;
   int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
+  int xpair;    // x-paired 32->32 conv run as 64->64 (see below): side taps are quarter blocks
+  uint32_t idesc_half;
   int vec256;   // output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int ksteps;   // k16 steps of a chunk that hold real channels (the rest are TMA zero fill: skipped)
   int patch_mode, b_resident, SA, SB;
@@ -176,6 +178,10 @@ struct ConvTcParams {
   uint32_t idesc;
 };
 
+// kx served by the i-th A patch of a channel chunk.  x-paired convs take the centre tap first: it is the only
+// one that writes all N columns, so it must be the MMA that zero-initialises the accumulator.
+__device__ __forceinline__ int patch_kx(int i, int xpair) { return xpair ? (i == 0 ? 1 : (i == 1 ? 0 : 2)) : i; }
+
 template <int CK>
 struct SwizzleCfg {
   static constexpr uint32_t kRowBytes = CK * 2;
@@ -184,9 +190,13 @@ struct SwizzleCfg {
   static constexpr uint32_t kLayout = CK == 64 ? 2u : (CK == 32 ? 4u : 6u);
 };
 
-template <int CK, typename T>
+// MODE bits (compile-time specialisation of the single-thread MMA issue loop)
+constexpr int MODE_PATCH = 1, MODE_RESIDENT = 2, MODE_XPAIR = 4;
+
+template <int CK, typename T, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using Cfg = SwizzleCfg<CK>;
+  constexpr bool PATCH = (MODE & MODE_PATCH) != 0, RESIDENT = (MODE & MODE_RESIDENT) != 0, XPAIR = (MODE & MODE_XPAIR) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int a = 0; a < nA; ++a) {
           int cc, view = 0, dy = 0, dx = 0, tap0;
           if (P.patch_mode) {           // one 18x16 box per (channel chunk, kx); rows y0-1 .. y0+16
-            cc = a / 3; const int kx = a % 3;
+            cc = a / 3; const int kx = patch_kx(a % 3, P.xpair);
             dy = -1; dx = kx - 1; tap0 = kx;
           } else {
             const int tap = a / P.cchunks; cc = a % P.cchunks; tap0 = tap;
@@ -290,63 +300,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    // (whole warp stays converged; one elected lane issues the tcgen05 instructions)
-    {
-      if (P.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    // ONE elected thread runs the whole issue loop.  It is a single dependent instruction stream, so every
+    // integer / branch instruction in it sits on the tensor pipe's critical path (ncu source view of the
+    // previous version: the issuing warp never waited for data, it spent ~110 clk per MMA pair on its own
+    // bookkeeping).  Hence: mode flags are template constants, the tap / k-step loops are fully unrolled,
+    // descriptors advance by adding constants to one 32-bit word.
+    if (RESIDENT) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    if (elect_one_sync()) {
       // descriptor words that never change (see make_smem_desc): hi = SBO | version | layout, lo = addr>>4 | LBO
       const uint32_t hi_a = (Cfg::kSBO_A >> 4) | (1u << 14) | (Cfg::kLayout << 29);
       const uint32_t hi_b = (Cfg::kAtom >> 4) | (1u << 14) | (Cfg::kLayout << 29);
       const uint32_t lo_flags = 1u << 16;
-      const uint32_t idesc = P.idesc, acc_stride = (uint32_t)P.acc_stride;
+      const uint32_t idesc = P.idesc, idesc_half = P.idesc_half, acc_stride = (uint32_t)P.acc_stride;
       const uint32_t b_block16 = P.b_block_bytes >> 4, a_stage16 = P.a_stage_bytes >> 4;
       const uint32_t a_lo_base = ((a_base >> 4) & 0x3FFF) | lo_flags, b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
-      const bool resident = P.b_resident != 0, patch = P.patch_mode != 0;
-      const int cchunks = P.cchunks, ksteps = P.ksteps;
+      const int cchunks = P.cchunks, ksteps = P.ksteps, taps = P.taps;
+      const bool full_k = ksteps == CK / 16;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
+      // the MMAs of one (A stage, tap): both halves of the super-tile, every k16 step of the chunk
+      auto issue = [&](uint32_t d0, uint32_t d1, uint32_t a_tap, uint32_t b_lo, uint32_t first, int kx) {
+        if (XPAIR && kx != 1) {
+          // side taps of the x-paired conv connect ONE pixel of the neighbouring pair to ONE of ours: a 32x32
+          // corner of the 64x64 block.  left pair (kx 0): K 32..63 -> N 0..31; right pair (kx 2): K 0..31 -> N 32..63
+          const int ks0 = kx == 0 ? 2 : 0;
+          const uint32_t dcol = kx == 0 ? 0u : 32u, brow = kx == 0 ? 0u : ((32u * Cfg::kRowBytes) >> 4);
+#pragma unroll
+          for (int ks = ks0; ks < ks0 + 2; ++ks) {
+            const uint32_t f = (ks == ks0) ? first : 1u;
+            umma_f16_lohi(d0 + dcol, a_tap + ks * 2, hi_a, b_lo + brow + ks * 2, hi_b, idesc_half, f);
+            umma_f16_lohi(d1 + dcol, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + brow + ks * 2, hi_b, idesc_half, f);
+          }
+        } else if (full_k) {   // one straight-line block: nothing between the MMAs but descriptor adds
+#pragma unroll
+          for (int ks = 0; ks < CK / 16; ++ks) {
+            const uint32_t f = (ks == 0) ? first : 1u;
+            umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);                        // left 8 columns
+            umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);  // right 8 columns
+          }
+        } else {               // 33/34-channel inputs: the zero-filled tail of the chunk is skipped
+#pragma unroll
+          for (int ks = 0; ks < CK / 16; ++ks) {
+            if (ks < ksteps) {
+              const uint32_t f = (ks == 0) ? first : 1u;
+              umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
+              umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
+            }
+          }
+        }
+      };
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;   // how often this buffer was used before
         mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator pair
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * 2u * acc_stride, d1 = d0 + acc_stride;
-        uint32_t accum = 0;
-        int cc = 0, t0 = 0;   // patch: (cc, kx) ; tap mode: (tap, cc)
-        for (int a = 0; a < nA; ++a) {
-          mbar_wait(fullA(sa), pha);
-          tc_fence_after();
-          const uint32_t a_lo = a_lo_base + (uint32_t)sa * a_stage16;
-          const int tap_first = patch ? t0 : t0;   // tap of sub 0 (patch: ky=0 -> tap = kx)
-#pragma unroll 1
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int tap = patch ? sub * 3 + tap_first : tap_first;
-            uint32_t b_lo;
-            if (resident) b_lo = b_lo_base + (uint32_t)(tap * cchunks + cc) * b_block16;
-            else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
-            const uint32_t a_tap = a_lo + (uint32_t)sub * (Cfg::kSBO_A >> 4);  // ky shift = one 16-pixel box row
-            if (elect_one_sync()) {
+        if (PATCH) {
+          // one A stage per (channel chunk, kx): rows y0-1 .. y0+16, the three ky taps are 16-pixel row shifts
+          for (int cc = 0; cc < cchunks; ++cc) {
 #pragma unroll
-              for (int ks = 0; ks < CK / 16; ++ks) {
-                if (ks >= ksteps) break;
-                const uint32_t acc_flag = (ks == 0) ? accum : 1u;
-                umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);                        // left 8 columns
-                umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, acc_flag);  // right 8 columns
+            for (int i = 0; i < 3; ++i) {
+              const int kx = XPAIR ? (i == 0 ? 1 : (i == 1 ? 0 : 2)) : i;
+              mbar_wait(fullA(sa), pha);
+              tc_fence_after();
+              const uint32_t a_lo = a_lo_base + (uint32_t)sa * a_stage16;
+#pragma unroll
+              for (int sub = 0; sub < 3; ++sub) {
+                uint32_t b_lo;
+                if (RESIDENT) b_lo = b_lo_base + (uint32_t)((sub * 3 + kx) * cchunks + cc) * b_block16;
+                else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
+                const uint32_t first = (i == 0 && sub == 0) ? (cc != 0 ? 1u : 0u) : 1u;
+                issue(d0, d1, a_lo + (uint32_t)sub * (Cfg::kSBO_A >> 4), b_lo, first, kx);
+                if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
               }
-              if (!resident) umma_commit(emptyB(sb));
-              if (sub == nsub - 1) umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
+              umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
+              if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
-            __syncwarp();
-            accum = 1u;  // only the very first k-step of each accumulator overwrites
-            if (!resident) { if (++sb == SB) { sb = 0; phb ^= 1u; } }
           }
-          if (++sa == SA) { sa = 0; pha ^= 1u; }
-          if (patch) { if (++t0 == 3) { t0 = 0; ++cc; } } else { if (++cc == cchunks) { cc = 0; ++t0; } }
+        } else {
+          // one A stage per (tap, channel chunk)
+          uint32_t first = 0u, b_res = b_lo_base;
+          for (int tap = 0; tap < taps; ++tap) {
+            for (int cc = 0; cc < cchunks; ++cc) {
+              mbar_wait(fullA(sa), pha);
+              tc_fence_after();
+              uint32_t b_lo;
+              if (RESIDENT) { b_lo = b_res; b_res += b_block16; }
+              else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
+              issue(d0, d1, a_lo_base + (uint32_t)sa * a_stage16, b_lo, first, 1);
+              first = 1u;
+              if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
+              umma_commit(emptyA(sa));
+              if (++sa == SA) { sa = 0; pha ^= 1u; }
+            }
+          }
         }
-        if (elect_one_sync()) umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
-        __syncwarp();
+        umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
       }
     }
+    __syncwarp();
   } else {
     // ========================================================================= epilogue
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
@@ -408,7 +461,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           float f[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bsrc + c0 + 4 * i);
+            const float4 b4 = P.bias_per_image ? *reinterpret_cast<const float4*>(bsrc + c0 + 4 * i)
+                                               : *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);   // LDS, not a generic load
             f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
             f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
           }
@@ -499,6 +553,8 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
                 "conv_tc: channel alignment");
   ACR_CHECK_ARG(a.in.dtype == act_dtype, "conv_tc: input dtype mismatch");
   ACR_CHECK_ARG(!(a.k == 1 && a.stride != 1), "conv_tc: 1x1 stride-2 unsupported");
+  ACR_CHECK_ARG(!a.xpair || (a.k == 3 && a.stride == 1 && a.cin_pad == 64 && a.cout_pad == 64 && a.in.pix_stride >= 64),
+                "conv_tc: the x-paired form is a 3x3 stride-1 64->64 conv");
   const int ck = (a.cin_pad % 64 == 0) ? 64 : ((a.cin_pad % 32 == 0) ? 32 : 16);
   ConvTcPlan* pl = new ConvTcPlan();
   ConvTcParams& p = pl->p;
@@ -542,6 +598,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   if (p.cchunks == 1 && (int)((dim0 + 15) / 16) < p.ksteps) p.ksteps = (int)((dim0 + 15) / 16);
   p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
   p.bias_per_image = a.bias_per_image; p.pow11_ch0 = a.pow11_ch0;
+  p.xpair = a.xpair;
   p.tiles_x = a.out.W / TILE_X; p.tiles_per_img = p.tiles_x * (a.out.H / TILE_Y);
   p.total_tiles = p.tiles_per_img * a.batch;
   p.Ho = a.out.H; p.Wo = a.out.W; p.out_stride = a.out.pix_stride;
@@ -555,6 +612,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N, M=128
   const uint32_t fmt = act_dtype == ACR_DT_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.cout_pad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  p.idesc_half = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   // shared-memory plan
   p.a_stage_bytes = (uint32_t)(box_rows * TILE_X) * ck * 2;
   p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
@@ -587,11 +645,11 @@ static bool pdl_enabled() {   // ACR_B200_PDL=0 disables programmatic dependent 
   return v != 0;
 }
 
-template <int CK, typename T>
+template <int CK, typename T, int MODE>
 static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -600,16 +658,31 @@ static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  ACR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<CK, T>, pl->p));
+  ACR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<CK, T, MODE>, pl->p));
   return ACR_B200_OK;
+}
+
+template <int CK, typename T>
+static int launch_mode(const ConvTcPlan* pl, cudaStream_t st) {
+  const int mode = (pl->p.patch_mode ? MODE_PATCH : 0) | (pl->p.b_resident ? MODE_RESIDENT : 0);
+  if (CK == 64 && pl->p.xpair) {
+    if (mode != (MODE_PATCH | MODE_RESIDENT)) { set_error("conv_tc: x-paired conv needs resident weights"); return ACR_B200_EINVAL; }
+    return launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR>(pl, st);
+  }
+  switch (mode) {
+    case 0: return launch_inst<CK, T, 0>(pl, st);
+    case 1: return launch_inst<CK, T, 1>(pl, st);
+    case 2: return launch_inst<CK, T, 2>(pl, st);
+    default: return launch_inst<CK, T, 3>(pl, st);
+  }
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t st) {
   const bool bf = pl->act_dtype == ACR_DT_BF16;
   switch (pl->ck) {
-    case 64: return bf ? launch_inst<64, __nv_bfloat16>(pl, st) : launch_inst<64, __half>(pl, st);
-    case 32: return bf ? launch_inst<32, __nv_bfloat16>(pl, st) : launch_inst<32, __half>(pl, st);
-    default: return bf ? launch_inst<16, __nv_bfloat16>(pl, st) : launch_inst<16, __half>(pl, st);
+    case 64: return bf ? launch_mode<64, __nv_bfloat16>(pl, st) : launch_mode<64, __half>(pl, st);
+    case 32: return bf ? launch_mode<32, __nv_bfloat16>(pl, st) : launch_mode<32, __half>(pl, st);
+    default: return bf ? launch_mode<16, __nv_bfloat16>(pl, st) : launch_mode<16, __half>(pl, st);
   }
 }
 

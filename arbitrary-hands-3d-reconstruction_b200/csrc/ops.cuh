@@ -15,6 +15,7 @@ struct ConvArgs {
   const void* w;           // [cout_pad][k*k][cin_pad] 16-bit
   const float* bias;       // [cout_pad] (or [B][cout_pad] when bias_per_image)
   int k, stride, relu, has_res, cin_pad, cout_pad, bias_per_image, pow11_ch0, batch;
+  int xpair;               // weights are the x-paired expansion of a 32->32 conv (ACR_CONV_XPAIR): side taps are 32x32 corners
 };
 
 struct FuseArgs {

@@ -36,6 +36,7 @@ static int make_conv_args(const acr_b200_op& op, int batch, char* arena, const c
   a->cin_pad = op.cin_pad; a->cout_pad = op.cout_pad; a->batch = batch;
   a->bias_per_image = (op.shift[0] & ACR_CONV_BIAS_PER_IMAGE) ? 1 : 0;
   a->pow11_ch0 = (op.shift[0] & ACR_CONV_POW11_CH0) ? 1 : 0;
+  a->xpair = (op.shift[0] & ACR_CONV_XPAIR) ? 1 : 0;
   if (a->bias_per_image) {
     ACR_CHECK_ARG(op.aux[0].dtype == ACR_DT_F32 && op.aux[0].pix_stride >= op.cout_pad, "conv: per-image bias tensor (aux[0]) malformed");
     a->bias = reinterpret_cast<const float*>(arena + op.aux[0].offset);

@@ -172,7 +172,7 @@ enum {
   ACR_OP_FINALCONV = 9,   /* (retired)                                                          */
   ACR_OP_IM2COL_STEM = 10 /* uint8 NHWC image -> 3x3 s2 im2col of x/255*2-1, 27(+5 zero) 16-bit channels */
 };
-enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2 };
+enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2, ACR_CONV_XPAIR = 4 };
 enum { ACR_DT_BF16 = 0, ACR_DT_F16 = 1, ACR_DT_F32 = 2, ACR_DT_U8 = 3 };
 
 typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image extents)  */
@@ -191,6 +191,9 @@ typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image
  *            [cout_pad][k*k][cin_pad], w_offset[1]=fp32 bias[cout_pad]; shift[0] = flag bits:
  *            ACR_CONV_BIAS_PER_IMAGE (bias = fp32 (B,cout_pad) tensor aux[0] in the arena instead of
  *            w_offset[1]) | ACR_CONV_POW11_CH0 (output channel 0 -> 1.1**x, acr/model.py:95-96)
+ *            | ACR_CONV_XPAIR (3x3 s1 64->64 whose weights are the x-paired expansion of a 32->32 conv: channel =
+ *            (x parity)*32 + c on a W/2 grid; the kx=0 / kx=2 taps are non-zero only in the [N 0..31][K 32..63] /
+ *            [N 32..63][K 0..31] corner, which is all the kernel multiplies)
  *  FUSE      in[0..n_in) with shift[i]; out
  *  BILINEAR2X / COORD (fparam unused; COORD writes channels [in[0].C, pix_stride) of `out`)
  *  POOL      in[0]=contact features (256ch), in[1]=segm logits; out = partials (fp32, 1x1xC)

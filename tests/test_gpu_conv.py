@@ -78,10 +78,12 @@ def test_conv_tc_full_resolution_property():
     assert (g1 - e1).abs().max().item() <= e1.abs().max().item() * 2e-5 + 1e-6
 
 
-def test_conv_tc_x_paired_32ch():
+@pytest.mark.parametrize("flags", [0, 4])
+def test_conv_tc_x_paired_32ch(flags):
     """The engine runs dense 32->32 3x3 convs as 64->64 convs on the x-paired grid (two adjacent pixels =
     one 128-byte operand row).  Packed through Engine._pack_conv(pair=True); expected from the ORIGINAL
-    weights with plain fp32 conv + BN + residual + ReLU."""
+    weights with plain fp32 conv + BN + residual + ReLU.  flags = ACR_CONV_XPAIR makes the kernel multiply only
+    the non-zero 32x32 corner of the two side taps (what the engine does); 0 = the full block-sparse weights."""
     import ctypes as C
     import torch.nn.functional as Fn
     from acr_b200.engine import Engine, _Blob
@@ -109,6 +111,7 @@ def test_conv_tc_x_paired_32ch():
     op.out = ctensor(2 * rup(nbytes, 1024), 64, H, W // 2, 64, L.DT_BF16)
     op.w_offset[0], op.w_offset[1] = w_off, b_off
     op.k, op.stride, op.relu, op.has_residual, op.cin_pad, op.cout_pad = 3, 1, 1, 1, 64, 64
+    op.shift[0] = flags
     d_arena = arena.cuda()
     d_blob = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).cuda()
     L.check(L.load().acr_b200_run_op(C.byref(op), B, d_arena.data_ptr(), d_blob.data_ptr(), None, L.DT_BF16,
