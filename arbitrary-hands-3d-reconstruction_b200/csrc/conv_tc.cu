@@ -87,6 +87,19 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA store of one [16 rows][8 px][64 ch] slab (shared -> global, bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -163,12 +176,16 @@ constexpr int SMEM_BUDGET = 224 * 1024;
 struct ConvTcParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmOut;   // output as {C, W, H, B}, box {64, 8, 16, 1}, 128B swizzle (tma_out)
   const float* bias;
   const void* res;
   void* out;
   int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
   int xpair;    // x-paired 32->32 conv run as 64->64 (see below): side taps are quarter blocks
   uint32_t idesc_half;
+  int debug;    // MODE_DIAG bits (0 in the product path)
+  int tma_out;  // epilogue stages 64-channel slabs in shared memory and stores them with TMA (16-bit, cout_pad % 64 == 0)
+  uint32_t stage_out_bytes;
   int vec256;   // output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int ksteps;   // k16 steps of a chunk that hold real channels (the rest are TMA zero fill: skipped)
   int patch_mode, b_resident, SA, SB;
@@ -192,18 +209,24 @@ struct SwizzleCfg {
 
 // MODE bits (compile-time specialisation of the single-thread MMA issue loop)
 constexpr int MODE_PATCH = 1, MODE_RESIDENT = 2, MODE_XPAIR = 4;
+// MODE_DIAG: diagnostic instances (tools/conv_bench.py, ACR_B200_CONV_DIAG=bits): 1 = the issuer skips the MMAs,
+// 2 = the epilogue only recycles the accumulator, 4 = the epilogue reads TMEM but skips math and stores.  Timing
+// floors of each warp role; never launched by the product path (debug == 0).
+constexpr int MODE_DIAG = 8;
 
 template <int CK, typename T, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using Cfg = SwizzleCfg<CK>;
   constexpr bool PATCH = (MODE & MODE_PATCH) != 0, RESIDENT = (MODE & MODE_RESIDENT) != 0, XPAIR = (MODE & MODE_XPAIR) != 0;
+  constexpr bool DIAG = (MODE & MODE_DIAG) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
   const int SA = P.SA, SB = P.SB;
   const uint32_t b_base = base;
   const uint32_t a_base = base + P.b_region_bytes;
-  const uint32_t bias_base = a_base + (uint32_t)SA * P.a_stage_bytes;   // fp32 bias[npad] (<= 1 KB)
+  const uint32_t stage_base = a_base + (uint32_t)SA * P.a_stage_bytes;  // epilogue staging: 2 halves x [128 px][128 B]
+  const uint32_t bias_base = stage_base + P.stage_out_bytes;            // fp32 bias[npad] (<= 1 KB)
   const uint32_t bar_base = bias_base + 1024u;
   // barrier map: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] bres tmem_full[2] tmem_empty[2] | tmem_ptr
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -230,6 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     fence_barrier_init();
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
+    if (P.tma_out) tma_prefetch_desc(&P.tmOut);
   }
   if (!P.bias_per_image)
     for (int i = threadIdx.x; i < P.npad; i += TC_THREADS) s_bias[i] = P.bias[i];
@@ -321,6 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int it = 0;
       // the MMAs of one (A stage, tap): both halves of the super-tile, every k16 step of the chunk
       auto issue = [&](uint32_t d0, uint32_t d1, uint32_t a_tap, uint32_t b_lo, uint32_t first, int kx) {
+        if (DIAG && (P.debug & 1)) return;
         if (XPAIR && kx != 1) {
           // side taps of the x-paired conv connect ONE pixel of the neighbouring pair to ONE of ours: a 32x32
           // corner of the 64x64 block.  left pair (kx 0): K 32..63 -> N 0..31; right pair (kx 2): K 0..31 -> N 32..63
@@ -405,6 +430,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
     const int h = (warp - 2) >> 2;         // which half (accumulator) of the super-tile
     const int r = q * 32 + lane;
+    // TMA-store path: a warp's direct stores put every lane on its own 128-byte line (32 LSU wavefronts per
+    // instruction -- ncu: l1tex data pipe 77 % busy, the epilogue was the bound of the N = 64 layers); staging
+    // the slab in swizzled shared memory costs 4 wavefronts per instruction and the TMA unit writes whole lines.
+    const bool tma_out = P.tma_out != 0;
+    const uint32_t stage_row = stage_base + (uint32_t)h * 16384u + (uint32_t)r * 128u;
+    const uint32_t stage_sw = (uint32_t)(r & 7);
     int it = 0;
     pdl_wait();   // residual / per-image bias reads and every output write wait for the previous kernel
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -413,6 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
       const int oy = (rem / P.tiles_x) * TILE_Y + (r >> 3), ox = (rem % P.tiles_x) * TILE_X + h * HALF_X + (r & 7);
       const size_t pix = ((size_t)n * P.Ho + oy) * P.Wo + ox;
+      const int ty0 = (rem / P.tiles_x) * TILE_Y, tx0 = (rem % P.tiles_x) * TILE_X + h * HALF_X;
       const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride : nullptr;
       // bias: per CTA from shared memory, or (folded part-head conv) one row per image from global
       const float* bsrc = P.bias_per_image ? P.bias + (size_t)n * P.npad : s_bias;
@@ -430,6 +462,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       mbar_wait(tmem_full(buf), use & 1u);
       tc_fence_after();
+      if (DIAG && (P.debug & 2)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(buf));
+        continue;
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
       for (int g0 = 0; g0 < P.npad; g0 += 64) {
         const int nch = min(4, (P.npad - g0) >> 4);  // 16-column chunks in this group (warp-uniform)
@@ -453,6 +491,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(buf));
+        }
+        if (DIAG && (P.debug & 4)) continue;
+        if (tma_out) {            // the previous slab's TMA store must have finished READING the staging buffer
+          if (r == 0) bulk_wait_read0();
+          named_bar_sync(1 + h, 128);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -484,16 +527,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
             T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + c0;
-            if (P.vec256) stg256(o, pack8<T>(f), pack8<T>(f + 8));
+            if (tma_out) {
+              sts128(stage_row + ((((uint32_t)(2 * c)) ^ stage_sw) << 4), pack8<T>(f));
+              sts128(stage_row + ((((uint32_t)(2 * c + 1)) ^ stage_sw) << 4), pack8<T>(f + 8));
+            } else if (P.vec256) stg256(o, pack8<T>(f), pack8<T>(f + 8));
             else {
               reinterpret_cast<uint4*>(o)[0] = pack8<T>(f);
               reinterpret_cast<uint4*>(o)[1] = pack8<T>(f + 8);
             }
           }
         }
+        if (tma_out) {   // slab complete in shared memory: one thread hands it to the TMA unit
+          fence_proxy_async_smem();
+          named_bar_sync(1 + h, 128);
+          if (r == 0) {
+            tma_store_4d(&P.tmOut, stage_base + (uint32_t)h * 16384u, g0, tx0, ty0, n);
+            bulk_commit();
+          }
+        }
       }
     }
   }
+  if (warp >= 2 && P.tma_out && ((warp & 3) * 32 + (threadIdx.x & 31)) == 0) bulk_wait_all();  // staging must outlive the stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -547,6 +602,14 @@ static int encode(CUtensorMap* m, int act_dtype, int rank, const void* ptr, cons
   return ACR_B200_OK;
 }
 
+// The TMA-store epilogue is opt-in (ACR_B200_TMA_OUT=1, read at plan creation): on B200 it measured 2 % slower per
+// step than direct 256-bit stores (two named barriers per slab and one A stage less outweigh the saved LSU
+// wavefronts), see DESIGN.md section 6.  It stays as a tested path for wider-N / store-bound layers.
+static bool tma_out_disabled() {
+  const char* e = getenv("ACR_B200_TMA_OUT");
+  return !(e && atoi(e) != 0);
+}
+
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x16 super-tile", a.out.H, a.out.W);
   ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 256,
@@ -589,6 +652,15 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)a.cout_pad};
     rc = encode(&p.tmB, act_dtype, 2, a.w, dims, str, box, ck);
   }
+  const bool want_tma_out = a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
+                            a.out.pix_stride % 8 == 0 && !tma_out_disabled();
+  if (!rc && want_tma_out) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.cout_pad, (cuuint64_t)a.out.W, (cuuint64_t)a.out.H, (cuuint64_t)a.batch};
+    cuuint64_t str[3] = {(cuuint64_t)a.out.pix_stride * esz, (cuuint64_t)a.out.W * a.out.pix_stride * esz,
+                         (cuuint64_t)a.out.H * a.out.W * a.out.pix_stride * esz};
+    cuuint32_t box[4] = {64, HALF_X, TILE_Y, 1};
+    rc = encode(&p.tmOut, act_dtype, 4, a.out.ptr, dims, str, box, 64);
+  }
   if (rc) { delete pl; return rc; }
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
@@ -599,6 +671,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
   p.bias_per_image = a.bias_per_image; p.pow11_ch0 = a.pow11_ch0;
   p.xpair = a.xpair;
+  { const char* e = getenv("ACR_B200_CONV_DIAG"); p.debug = e ? atoi(e) : 0; }
   p.tiles_x = a.out.W / TILE_X; p.tiles_per_img = p.tiles_x * (a.out.H / TILE_Y);
   p.total_tiles = p.tiles_per_img * a.batch;
   p.Ho = a.out.H; p.Wo = a.out.W; p.out_stride = a.out.pix_stride;
@@ -617,7 +690,9 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.a_stage_bytes = (uint32_t)(box_rows * TILE_X) * ck * 2;
   p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
   const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
-  const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/;
+  p.tma_out = want_tma_out ? 1 : 0;
+  p.stage_out_bytes = p.tma_out ? 2u * 16384u : 0u;
+  const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
   const int nA = p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks;
   p.b_resident = (b_total + 3 * (size_t)p.a_stage_bytes + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
   if (p.b_resident) {
@@ -665,6 +740,11 @@ static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
 template <int CK, typename T>
 static int launch_mode(const ConvTcPlan* pl, cudaStream_t st) {
   const int mode = (pl->p.patch_mode ? MODE_PATCH : 0) | (pl->p.b_resident ? MODE_RESIDENT : 0);
+  if (pl->p.debug) {
+    if (CK != 64 || mode != (MODE_PATCH | MODE_RESIDENT)) { set_error("conv_tc: diagnostic instances exist for CK=64 patch/resident only"); return ACR_B200_EINVAL; }
+    return pl->p.xpair ? launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR | MODE_DIAG>(pl, st)
+                       : launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_DIAG>(pl, st);
+  }
   if (CK == 64 && pl->p.xpair) {
     if (mode != (MODE_PATCH | MODE_RESIDENT)) { set_error("conv_tc: x-paired conv needs resident weights"); return ACR_B200_EINVAL; }
     return launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR>(pl, st);

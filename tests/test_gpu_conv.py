@@ -55,6 +55,14 @@ def test_conv_tc(case):
     _check(L.OP_CONV, case)
 
 
+@pytest.mark.parametrize("case", [CASES[1], CASES[3], CASES[4], CASES[5]])
+def test_conv_tc_tma_store_epilogue(case, monkeypatch):
+    """Opt-in epilogue that stages 64-channel slabs in swizzled shared memory and writes them with TMA stores
+    (ACR_B200_TMA_OUT=1 at plan creation): same results as the direct-store epilogue."""
+    monkeypatch.setenv("ACR_B200_TMA_OUT", "1")
+    _check(L.OP_CONV, case)
+
+
 @pytest.mark.parametrize("case", CASES[:4])
 def test_conv_tc_fp16(case):
     _check(L.OP_CONV, case, dt=L.DT_F16)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Time single conv ops through the C ABI (acr_b200_run_op via a 1-op plan) at full batch.
-    python tools/conv_bench.py "32,32,3,1,128,1" "64,64,3,1,64,0" ...   (cin,cout,k,s,H,residual)"""
+    python tools/conv_bench.py "32,32,3,1,128,1" "64,64,3,1,64,0" ...   (cin,cout,k,s,H,residual[,W[,flags]])
+W defaults to H; flags = conv flag bits (4 = ACR_CONV_XPAIR).  ACR_B200_CONV_DIAG=1|2|4 times the diagnostic
+kernel instances (issuer without MMAs / epilogue only recycling / epilogue without math and stores)."""
 import ctypes as C
 import os
 import sys
@@ -16,11 +18,14 @@ from tests.helpers import ctensor, rup  # noqa: E402
 B = int(os.environ.get("BATCH", "256"))
 lib = L.load()
 for spec in sys.argv[1:]:
-    cin, cout, k, s, H, res = (int(v) for v in spec.split(","))
+    fields = [int(v) for v in spec.split(",")]
+    cin, cout, k, s, H, res = fields[:6]
+    W = fields[6] if len(fields) > 6 else H
+    flags = fields[7] if len(fields) > 7 else 0
     cin_pad, cout_pad = rup(cin, 16), rup(cout, 16)
-    Ho = H // s
-    in_bytes = B * H * H * cin_pad * 2
-    out_bytes = B * Ho * Ho * cout_pad * 2
+    Ho, Wo = H // s, W // s
+    in_bytes = B * H * W * cin_pad * 2
+    out_bytes = B * Ho * Wo * cout_pad * 2
     off_r = rup(in_bytes, 1024)
     off_o = rup(off_r + out_bytes, 1024)
     arena = (torch.randn((off_o + out_bytes) // 2 + 512, device="cuda") * 0.5).to(torch.bfloat16)
@@ -31,9 +36,10 @@ for spec in sys.argv[1:]:
     op = L.Op()
     op.kind = L.OP_CONV
     op.n_in = 2 if res else 1
-    op.in_[0] = ctensor(0, cin, H, H, cin_pad, L.DT_BF16)
-    op.in_[1] = ctensor(off_r, cout, Ho, Ho, cout_pad, L.DT_BF16)
-    op.out = ctensor(off_o, cout, Ho, Ho, cout_pad, L.DT_BF16)
+    op.in_[0] = ctensor(0, cin, H, W, cin_pad, L.DT_BF16)
+    op.in_[1] = ctensor(off_r, cout, Ho, Wo, cout_pad, L.DT_BF16)
+    op.out = ctensor(off_o, cout, Ho, Wo, cout_pad, L.DT_BF16)
+    op.shift[0] = flags
     op.w_offset[0], op.w_offset[1] = 0, bias_off
     op.k, op.stride, op.relu, op.has_residual = k, s, 1, res
     op.cin_pad, op.cout_pad = cin_pad, cout_pad
@@ -54,7 +60,7 @@ for spec in sys.argv[1:]:
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
-    fl = 2.0 * Ho * Ho * cout * cin * k * k * B
+    fl = 2.0 * Ho * Wo * cout * cin * k * k * B
     by = in_bytes + out_bytes * (2 if res else 1)
     print(f"{spec:>22s}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s (algorithmic)", flush=True)
     lib.acr_b200_plan_destroy(plan)

@@ -1,0 +1,18 @@
+#!/bin/bash
+# ncu evidence for the conv kernel (run on the GPU box through gpurun; outputs under gpurun_out/):
+#   1. launch list of one whole step (gpu__time_duration.sum per launch)
+#   2. --set full + source of one x-paired 32->32 launch (MODE 7) and one 64->64 patch/resident launch (MODE 3)
+set -u
+TAG=${1:-r1_v13}
+OUT=gpurun_out
+mkdir -p $OUT
+L=$(python tools/profile_step.py --batch 256 --steps 1 | grep "launches per step" | awk '{print $4}')
+echo "launches per step: $L"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s "$L" -c "$L" --csv \
+    --log-file $OUT/launches_${TAG}.csv python tools/profile_step.py --batch 256 > $OUT/prof_list.log 2>&1
+for MODE in 7 3; do
+  timeout 600 ncu --set full --import-source on --clock-control none --kernel-name-base demangled \
+      -k "regex:conv_tc_kernel<\(int\)64, __nv_bfloat16, \(int\)${MODE}>" -s 40 -c 1 -f \
+      -o $OUT/conv_tc_${TAG}_mode${MODE} python tools/profile_step.py --batch 256 > $OUT/prof_full_${MODE}.log 2>&1
+done
+ls -la $OUT | tail -5
