@@ -475,17 +475,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < nch) tmem_ld16(t_row + (uint32_t)(g0 + c * 16), v[c]);
-        if (resp && g0 > 0) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < nch) {
-              if (P.vec256) ldg256(resp + g0 + c * 16, rr[c][0], rr[c][1]);
-              else {
-                rr[c][0] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16);
-                rr[c][1] = *reinterpret_cast<const uint4*>(resp + g0 + c * 16 + 8);
-              }
-            }
-        }
         tmem_ld_wait();
         if (g0 + 64 >= P.npad) {  // all TMEM reads of this tile done: hand the accumulator back
           tc_fence_before();
@@ -516,6 +505,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             unpack8<T>(rr[c][1], x + 8);
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] += x[i];
+            // this chunk's residual registers are free again: fetch the same chunk of the NEXT 64-channel group now,
+            // so that its DRAM round trip overlaps the rest of this group (wide layers are HBM bound)
+            if (c0 + 64 < P.npad) {
+              if (P.vec256) ldg256(resp + c0 + 64, rr[c][0], rr[c][1]);
+              else {
+                rr[c][0] = *reinterpret_cast<const uint4*>(resp + c0 + 64);
+                rr[c][1] = *reinterpret_cast<const uint4*>(resp + c0 + 64 + 8);
+              }
+            }
           }
           if (P.relu) {
 #pragma unroll

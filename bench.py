@@ -275,16 +275,18 @@ def run_b200(args):
     n_hands = int(bufs.counts[2])
     if rank == 0:
         peaks = load_peaks()
-        traffic = None
+        traffic, alg_gb = None, None
         try:   # DRAM bytes of the conv launch set from the committed ncu capture (same batch / build family)
             with open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")) as f:
                 tj = json.load(f)
             if B == 256:
-                traffic = tj["traffic_bytes"]
+                traffic, alg_gb = tj["traffic_bytes"], tj["algorithmic_bytes"] / 1e9
         except Exception:
             pass
         conv_gflop = sum(2.0 * o.out.H * o.out.W * o.out.C * o.ins[0].C * o.attrs["k"] ** 2
                          for o in eng.spec.ops if o.kind == "conv") / 1e9
+        if eng.stem_on_tensor_cores:   # conv1 (3x3 s2, 3 -> 64) runs as im2col + a 1x1 tcgen05 conv: 27 real taps
+            conv_gflop += sum(2.0 * o.out.H * o.out.W * 64 * 27 for o in eng.spec.ops if o.kind == "stem") / 1e9
         ach = conv_gflop * B / conv_ms if conv_ms else 0.0          # TFLOP/s (GFLOP/ms)
         img_s = world * B * args.steps / (ms_value / 1e3)
         e2e_s = world * B * args.steps / (ms_e2e / 1e3)
@@ -307,7 +309,7 @@ def run_b200(args):
                          "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": ach / peaks["tf_sustained"] if ach else 0.0, "traffic": traffic,
                          "traffic_note": "DRAM read+write bytes of the whole conv launch set per step, ncu capture "
-                                         "profiles/r1_conv_traffic.json (algorithmic: 163.5 GB)",
+                                         "profiles/r1_conv_traffic.json" + (f" (algorithmic: {alg_gb:.1f} GB)" if alg_gb else ""),
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "algorithmic_gflop_per_launch_set": conv_gflop * B,
                          "conv_ms_per_step": conv_ms, "conv_share_of_plan": conv_ms / total_prof_ms if total_prof_ms else None,

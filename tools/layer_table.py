@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Per-layer-class conv timing table from an ncu launch list (gpu__time_duration.sum CSV)."""
+"""Tables from ncu CSVs of one step (tools/ncu_conv.sh):
+    python tools/layer_table.py kernels <launch list csv>          per-kernel totals (gpu__time_duration.sum)
+    python tools/layer_table.py convs <conv traffic csv> [batch]   per-layer-class conv table: time, TFLOP/s, measured
+                                                                   DRAM GB/s and tensor-pipe activity"""
 import collections
 import csv
 import os
@@ -10,34 +13,53 @@ sys.path.insert(0, os.path.join(ROOT, "arbitrary-hands-3d-reconstruction_b200"))
 from acr_b200 import lib as L  # noqa: E402
 from acr_b200.engine import Engine  # noqa: E402
 
-path, batch = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 256
-lines = [l for l in open(path) if not l.startswith("==")]
-rows = [(r["Kernel Name"], float(r["Metric Value"].replace(",", "")), r["Grid Size"]) for r in csv.DictReader(lines)
-        if r.get("Metric Name") == "gpu__time_duration.sum"]
-stems = [i for i, r in enumerate(rows) if "stem_kernel" in r[0]]
-step = rows[stems[-1]:]
-tot = sum(r[1] for r in step)
-agg = collections.OrderedDict()
-for name, ns, grid in step:
-    a = agg.setdefault(name.split("(")[0], [0, 0.0])
-    a[0] += 1
-    a[1] += ns
-print("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"| `{k}` | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.1f}% |")
-print(f"| **total** | {len(step)} | {tot / 1e6:.3f} | 100% |\n")
-convs = [r for r in step if "conv_tc" in r[0]]
-cops = [r for r in Engine(None, 1, "cpu", dry_run=True).recs if r["kind"] == L.OP_CONV]
-assert len(cops) == len(convs), (len(cops), len(convs))
-agg = collections.OrderedDict()
-for r, (name, ns, grid) in zip(cops, convs):
-    x, y, at = r["ins"][0], r["out"], r["attrs"]
-    cin = 109 if "fold_side" in at else x.C
-    key = (cin, y.C, at["k"], at["s"], x.H, bool(at["residual"]))
-    a = agg.setdefault(key, [0, 0.0, 0.0])
-    a[0] += 1
-    a[1] += ns
-    a[2] += 2.0 * y.H * y.W * y.C * cin * at["k"] ** 2 * batch
-print("| cin | cout | k | s | H_in | res | n | total ms | avg us | TFLOP/s |\n|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"| {k[0]} | {k[1]} | {k[2]} | {k[3]} | {k[4]} | {'y' if k[5] else ''} | {v[0]} | {v[1] / 1e6:.2f} | {v[1] / v[0] / 1e3:.0f} | {v[2] / v[1] / 1e3:.0f} |")
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "%": 1.0}
+
+
+def launches(path):
+    per = collections.OrderedDict()
+    for r in csv.DictReader(l for l in open(path) if not l.startswith("==")):
+        d = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
+    return list(per.values())
+
+
+mode, path = sys.argv[1], sys.argv[2]
+rows = launches(path)
+if mode == "kernels":
+    rows = [r for r in rows if "acr::" in r["name"]]
+    tot = sum(r["gpu__time_duration.sum"] for r in rows)
+    agg = collections.OrderedDict()
+    for r in rows:
+        a = agg.setdefault(r["name"].split("(")[0], [0, 0.0])
+        a[0] += 1
+        a[1] += r["gpu__time_duration.sum"]
+    print("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.1f}% |")
+    print(f"| **total** | {len(rows)} | {tot / 1e6:.3f} | 100% |")
+else:
+    batch = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    cops = [r for r in Engine(None, 1, "cpu", dry_run=True).recs if r["kind"] == L.OP_CONV]
+    assert len(cops) == len(rows), (len(cops), len(rows))
+    agg = collections.OrderedDict()
+    for r, m in zip(cops, rows):
+        x, y, at = r["ins"][0], r["out"], r["attrs"]
+        cin = 109 if "fold_side" in at else (27 if "stem" in at else x.C)
+        key = (cin, y.C, at["k"], at["s"], x.H, bool(at["residual"]))
+        a = agg.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        ns = m["gpu__time_duration.sum"]
+        a[0] += 1
+        a[1] += ns
+        a[2] += 2.0 * y.H * y.W * y.C * cin * at["k"] ** 2 * batch
+        a[3] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
+        a[4] += ns * m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
+        a[5] += batch * (x.H * x.W * x.C * 2 + y.H * y.W * y.C * (4 if y.dtype == "f32" else 2) * (2 if at["residual"] else 1))
+    print("| cin | cout | k | s | H_in | res | n | total ms | avg us | TFLOP/s | DRAM GB/s (measured) | DRAM / algorithmic bytes | tensor pipe active |")
+    print("|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| {k[0]} | {k[1]} | {k[2]} | {k[3]} | {k[4]} | {'y' if k[5] else ''} | {v[0]} | {v[1] / 1e6:.2f} | {v[1] / v[0] / 1e3:.0f} | "
+              f"{v[2] / v[1] / 1e3:.0f} | {v[3] / v[1]:.0f} | {v[3] / v[5]:.2f} | {v[4] / v[1]:.0f}% |")
+    t = sum(v[1] for v in agg.values())
+    print(f"\ntotal {t / 1e6:.2f} ms over {len(rows)} launches, {sum(v[2] for v in agg.values()) / t / 1e3:.0f} TFLOP/s, "
+          f"DRAM {sum(v[3] for v in agg.values()) / 1e9:.1f} GB ({sum(v[3] for v in agg.values()) / t:.0f} GB/s)")

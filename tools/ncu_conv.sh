@@ -10,6 +10,15 @@ L=$(python tools/profile_step.py --batch 256 --steps 1 | grep "launches per step
 echo "launches per step: $L"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s "$L" -c "$L" --csv \
     --log-file $OUT/launches_${TAG}.csv python tools/profile_step.py --batch 256 > $OUT/prof_list.log 2>&1
+NC=$(python -c "
+import sys; sys.path.insert(0, 'arbitrary-hands-3d-reconstruction_b200')
+from acr_b200 import lib as L; from acr_b200.engine import Engine
+print(sum(1 for r in Engine(None, 1, 'cpu', dry_run=True).recs if r['kind'] == L.OP_CONV))")
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
+    --clock-control none -k regex:conv_tc -s "$NC" -c "$NC" --csv --log-file $OUT/conv_traffic_${TAG}.csv \
+    python tools/profile_step.py --batch 256 > $OUT/prof_traffic.log 2>&1
+python tools/conv_traffic.py $OUT/conv_traffic_${TAG}.csv $OUT/conv_traffic_${TAG}.json
+[ "${FULL:-1}" = "1" ] || exit 0
 for MODE in 7 3; do
   timeout 600 ncu --set full --import-source on --clock-control none --kernel-name-base demangled \
       -k "regex:conv_tc_kernel<\(int\)64, __nv_bfloat16, \(int\)${MODE}>" -s 40 -c 1 -f \
