@@ -27,7 +27,7 @@ def launches(path):
 mode, path = sys.argv[1], sys.argv[2]
 rows = launches(path)
 if mode == "kernels":
-    rows = [r for r in rows if "acr::" in r["name"]]
+    rows = [r for r in rows if "at::" not in r["name"]]   # drop torch helper kernels (fills, copies)
     tot = sum(r["gpu__time_duration.sum"] for r in rows)
     agg = collections.OrderedDict()
     for r in rows:

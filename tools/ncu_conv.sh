@@ -8,8 +8,9 @@ OUT=gpurun_out
 mkdir -p $OUT
 L=$(python tools/profile_step.py --batch 256 --steps 1 | grep "launches per step" | awk '{print $4}')
 echo "launches per step: $L"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s "$L" -c "$L" --csv \
-    --log-file $OUT/launches_${TAG}.csv python tools/profile_step.py --batch 256 > $OUT/prof_list.log 2>&1
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $OUT/launches_${TAG}.csv python tools/profile_step.py --batch 256 --range > $OUT/prof_list.log 2>&1
+[ "${LIST_ONLY:-0}" = "1" ] && exit 0
 NC=$(python -c "
 import sys; sys.path.insert(0, 'arbitrary-hands-3d-reconstruction_b200')
 from acr_b200 import lib as L; from acr_b200.engine import Engine

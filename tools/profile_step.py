@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One warm-up step + one profiled step of the hot path, for ncu:
-    ncu --metrics gpu__time_duration.sum --clock-control none -s <L> -c <L> --csv --log-file ... \\
-        python tools/profile_step.py --batch 256          (L = launches per step, printed below)
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file ... \\
+        python tools/profile_step.py --batch 256 --range      (cudaProfilerStart/Stop around the LAST step)
 """
 import argparse
 import os
@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--range", action="store_true", help="cudaProfilerStart/Stop around the last step")
 a = ap.parse_args()
 from acr.config import args as cfg  # noqa: E402
 from acr.main import ACR  # noqa: E402
@@ -28,7 +29,12 @@ app = ACR(state_dict=synth_state_dict(0, bn_stats=load_bn_calibration(0)),
 g = torch.Generator().manual_seed(0)
 frames = torch.randint(0, 256, (a.batch, 512, 512, 3), generator=g, dtype=torch.uint8).cuda()
 offs = torch.tensor([[512., 512, 0, 0, 0, 0, 0, 0, 0, 0]]).repeat(a.batch, 1).cuda()
-for _ in range(a.steps):
+for i in range(a.steps):
+    last = a.range and i == a.steps - 1
+    if last:
+        torch.cuda.cudart().cudaProfilerStart()
     app.fused_forward(frames, offs)
     torch.cuda.synchronize()
+    if last:
+        torch.cuda.cudart().cudaProfilerStop()
 print("launches per step:", app.model.engine(a.batch, frames.device).num_launches + 4)
