@@ -34,6 +34,20 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (kernel instance, device): the attribute is
+// per device, and one process may drive several (`done` is the caller's static per-instance device bit mask).
+template <typename Kernel>
+static inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+  return e;
+}
+
 // ---- 16-bit activation type helpers ------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -720,11 +720,8 @@ static bool pdl_enabled() {   // ACR_B200_PDL=0 disables programmatic dependent 
 
 template <int CK, typename T, int MODE>
 static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ACR_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CK, T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  ACR_CHECK_CUDA(ensure_dynamic_smem(conv_tc_kernel<CK, T, MODE>, SMEM_BUDGET, &configured));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl->smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

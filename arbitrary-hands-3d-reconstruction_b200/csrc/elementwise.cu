@@ -515,11 +515,8 @@ int launch_pool(const TensorRef& feat, const TensorRef& logits, float* part, int
                     (feat.H * feat.W) % POOL_CHUNKS == 0 && per % POOL_HALF == 0 &&
                     feat.pix_stride % 8 == 0, "pool: shapes");
   ACR_DISPATCH_ACT(act_dtype, {
-    static bool attr_set = false;
-    if (!attr_set) {
-      ACR_CHECK_CUDA(cudaFuncSetAttribute(pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM_BYTES));
-      attr_set = true;
-    }
+    static unsigned long long attr_set = 0;
+    ACR_CHECK_CUDA(ensure_dynamic_smem(pool_kernel<T>, POOL_SMEM_BYTES, &attr_set));
     pool_kernel<T><<<dim3(batch, POOL_CHUNKS), 256, POOL_SMEM_BYTES, st>>>(feat, logits, part);
   });
   ACR_CHECK_LAUNCH();

@@ -99,3 +99,39 @@ def test_product_path_fails_loudly_without_cuda():
     from acr_b200.engine import Engine
     with pytest.raises(L.AcrB200Error):
         Engine({}, 1, "cpu")
+
+
+def test_xpair_weight_expansion_has_the_corners_the_kernel_multiplies(lib):
+    """ACR_CONV_XPAIR: the conv kernel only multiplies the [N 0..31][K 32..63] corner of the kx=0 taps and the
+    [N 32..63][K 0..31] corner of the kx=2 taps of an x-paired 32->32 conv.  Everything it skips must be zero in
+    the packed weights, and the centre taps must be what they were (engine._pack_conv(pair=True))."""
+    from acr_b200.engine import Engine, _Blob
+    rng = np.random.default_rng(5)
+    sd = {"c.weight": rng.standard_normal((32, 32, 3, 3)).astype(np.float32)}
+    eng = Engine(None, 1, "cpu", dry_run=True)
+    blob = _Blob()
+    w_off, _ = eng._pack_conv(sd, blob, "c", None, False, 64, 64, pair=True)
+    wp = np.frombuffer(blob.tobytes(), np.uint16, count=64 * 9 * 64, offset=w_off).reshape(64, 3, 3, 64)  # [n][ky][pt][k]
+    left, centre, right = wp[:, :, 0, :], wp[:, :, 1, :], wp[:, :, 2, :]
+    assert not left[32:].any() and not left[:, :, :32].any() and left[:32, :, 32:].all()
+    assert not right[:32].any() and not right[:, :, 32:].any() and right[32:, :, :32].all()
+    assert centre.all()
+    # even output pixel <- odd pixel of the left pair through the original kx = 0 tap (bf16-rounded)
+    ref = torch.from_numpy(sd["c.weight"][:, :, :, 0]).bfloat16().view(torch.int16).numpy().view(np.uint16)   # [co][ci][ky]
+    assert (left[:32, :, 32:] == ref.transpose(0, 2, 1)).all()
+
+
+def test_plan_records_of_the_engine():
+    """Launch-plan shape of the whole network (dry run, no GPU): op kinds, tensor-core stem, x-paired convs."""
+    from acr_b200.engine import Engine
+    eng = Engine(None, 2, "cpu", dry_run=True)
+    kinds = [r["kind"] for r in eng.recs]
+    assert kinds.count(L.OP_CONV) == 347 and kinds.count(L.OP_IM2COL_STEM) == 1 and kinds.count(L.OP_STEM) == 0
+    assert kinds.count(L.OP_FUSE) == 23 and kinds.count(L.OP_POOL) == 1 and kinds.count(L.OP_PARTHEAD) == 1
+    assert eng.n_ops == len(kinds) == 375
+    assert eng.arena_bytes == 2 * 26 * 2 ** 20
+    c32 = [r for r in eng.recs if r["kind"] == L.OP_CONV and r["attrs"]["k"] == 3 and r["attrs"]["s"] == 1
+           and r["ins"][0].C == 32 and r["out"].C == 32 and r["ins"][0].H == 128]
+    assert len(c32) == 64                                  # the x-paired class: 32 BasicBlocks of branch 0
+    old = Engine(None, 2, "cpu", dry_run=True, stem_on_tensor_cores=False)
+    assert [r["kind"] for r in old.recs].count(L.OP_STEM) == 1 and old.n_ops == 374
