@@ -124,6 +124,27 @@ def test_plan_tcgen05_matches_refconv(sd, image):
         assert rel_err(a[k].numpy(), b[k].numpy()) < 2e-2, k
 
 
+def test_full_batch_256_is_batch_invariant(sd, image):
+    """BASELINE configs[2] size (256 frames per GPU) through a size-independent property: every kernel of the plan
+    works per image (conv super-tiles, pooling chunks, part head), so a frame's maps must not depend on the
+    batch it travels in -- the 256-frame plan run on the two test frames repeated 128 times reproduces the
+    2-frame plan (itself pinned against the oracle above) bit for bit, at every position of the batch."""
+    from acr_b200.engine import Engine
+    B = 256
+    names = ["segms", "l_center_map", "r_center_map", "l_params_maps", "r_params_maps", "l_prior_maps", "r_prior_maps"]
+    small = Engine(sd, 2, "cuda")
+    small.run(image.cuda())
+    frames = image[torch.arange(B) % 2].contiguous().cuda()
+    big = Engine(sd, B, "cuda")
+    big.run(frames)
+    torch.cuda.synchronize()
+    for n in names + ["pooled"]:
+        C = big.spec.tensors[n].C                      # logical channels (the rest of the pixel stride is padding)
+        a, b = big.view(n)[..., :C], small.view(n)[..., :C]
+        a = a.reshape(B // 2, 2, *a.shape[1:])
+        assert torch.equal(a, b.unsqueeze(0).expand_as(a)), n
+
+
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_dropin_api_end_to_end(sd, image, precision):
     """acr.main.ACR -> acr.model.ACR.forward -> MANOWrapper.forward against (a) the oracle run on the
