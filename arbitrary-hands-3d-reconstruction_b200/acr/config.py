@@ -15,7 +15,8 @@ project_dir = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__fil
 
 _DEFAULTS = dict(
     tab="ACR_hrnet_internet", backbone="hrnet",          # config.py:95 (flag is only a log tag)
-    model_precision="bf16",                               # reference: fp32|fp16 (config.py:96); B200 path: bf16|fp16
+    model_precision="bf16",                               # reference: fp32|fp16 (config.py:96); here bf16|fp16 = tensor-core
+                                                          # plans, fp32 = the (slow, reference-accurate) validation plan
     input_size=512,                                        # config.py:61
     centermap_size=64, centermap_conf_thresh=0.35,         # config.py:130-131
     kernel_sizes=[5], max_hand=4,                          # config.py:185,161

@@ -45,25 +45,32 @@ class ResultParser(nn.Module):
 
     @staticmethod
     def collect(bufs, outputs, meta_data):
-        """One D2H read of (L, R), then slice the buffers into the reference's output schema."""
+        """One D2H read of (L, R), then copy the N valid rows of the (per batch size cached, worst-case sized)
+        parse buffers into fresh tensors with the reference's output schema.  Like the reference, every call
+        returns its own tensors: a later forward() does not overwrite them and the in-place temporal smoothing
+        of acr.main works on this call's rows only.  (The sync-free ``forward_dense`` / ``fused_forward`` path
+        hands out the shared buffers themselves -- zero copy -- and documents that.)"""
         L, R = (int(v) for v in bufs.counts[:2].tolist())
         N = L + R
-        outputs['params_pred'] = bufs.params_pred[:N]
-        outputs['l_params_pred'], outputs['r_params_pred'] = bufs.params_pred[:L], bufs.params_pred[L:N]
-        outputs['detection_flag'] = bufs.detection_flag[:N]
-        outputs['detection_flag_cache'] = bufs.detection_flag[:N].bool()
-        outputs['l_centers_pred'], outputs['r_centers_pred'] = bufs.centers_pred[:L], bufs.centers_pred[L:N]
-        outputs['l_centers_conf'] = bufs.centers_conf[:L].unsqueeze(1)
-        outputs['r_centers_conf'] = bufs.centers_conf[L:N].unsqueeze(1)
+        own = lambda t: t[:N].clone()
+        params_pred = own(bufs.params_pred)
+        outputs['params_pred'] = params_pred
+        outputs['l_params_pred'], outputs['r_params_pred'] = params_pred[:L], params_pred[L:N]
+        outputs['detection_flag'] = own(bufs.detection_flag)
+        outputs['detection_flag_cache'] = outputs['detection_flag'].bool()
+        centers, conf = own(bufs.centers_pred), own(bufs.centers_conf)
+        outputs['l_centers_pred'], outputs['r_centers_pred'] = centers[:L], centers[L:N]
+        outputs['l_centers_conf'] = conf[:L].unsqueeze(1)
+        outputs['r_centers_conf'] = conf[L:N].unsqueeze(1)
         dev = bufs.counts.device
         outputs['left_hand_num'] = torch.tensor([L], device=dev)
         outputs['right_hand_num'] = torch.tensor([R], device=dev)
-        outputs['reorganize_idx'] = bufs.reorganize_idx[:N]
-        outputs['output_hand_type'] = bufs.hand_type[:N]
-        outputs['params_dict'] = dict(cam=bufs.cam[:N], global_orient=bufs.global_orient[:N],
-                                      hand_pose=bufs.hand_pose[:N], betas=bufs.betas[:N], poses=bufs.poses[:N])
+        outputs['reorganize_idx'] = own(bufs.reorganize_idx)
+        outputs['output_hand_type'] = own(bufs.hand_type)
+        outputs['params_dict'] = dict(cam=own(bufs.cam), global_orient=own(bufs.global_orient),
+                                      hand_pose=own(bufs.hand_pose), betas=own(bufs.betas), poses=own(bufs.poses))
         if meta_data is not None:
-            bi = bufs.batch_ids[:N]
+            bi = own(bufs.batch_ids)
             for key in ('image', 'offsets', 'imgpath'):      # result_parser.py:186-187
                 if key in meta_data:
                     v = meta_data[key]

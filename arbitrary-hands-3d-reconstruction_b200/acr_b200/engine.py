@@ -84,31 +84,45 @@ class Engine:
     """The backbone + heads of ACR as one precompiled CUDA launch plan.
 
     ``state_dict`` uses the reference's key names (checkpoint compatible).  ``act_dtype`` is
-    torch.bfloat16 or torch.float16 (storage of activations/weights; accumulation is fp32).
+    torch.bfloat16 or torch.float16 (storage of activations/weights; accumulation is fp32) -- the
+    product path on the tensor cores -- or torch.float32: the VALIDATION plan (fp32 storage, fp64
+    accumulation on the CUDA cores, csrc/validate_f32.cu), which is what the reference's default
+    ``model_precision='fp32'`` maps to and what pins the whole pipeline at 1e-4.
     ``debug_ref_conv`` swaps the tcgen05 conv for the CUDA-core reference kernel (tests only).
+    ``head_only`` builds the plan of ``ACR.head_forward`` (/root/reference/acr/model.py:47-65): the ops
+    after the trunk, fed by an external (B,32,H/4,W/4) feature through ``run_heads``.
+    ``weights`` re-uses the packed weight blob of another engine of the same dtype / flags (the blob does
+    not depend on the batch size).
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, device, act_dtype=torch.bfloat16,
                  input_size: int = 512, debug_ref_conv: bool = False, reuse_memory: bool = True,
-                 dry_run: bool = False, keep_extra=(), stem_on_tensor_cores: bool = True):
+                 dry_run: bool = False, keep_extra=(), stem_on_tensor_cores: bool = True,
+                 head_only: bool = False, weights: Optional[torch.Tensor] = None):
         self.keep_extra = tuple(keep_extra)   # extra tensor names kept alive after the run (tests)
-        self.stem_on_tensor_cores = stem_on_tensor_cores
         self.dry_run = dry_run      # layout only (arena size, op list); used by CPU tests
         if not dry_run and not torch.cuda.is_available():
             raise L.AcrB200Error("Engine needs a CUDA device; there is no CPU fallback on the product path")
         self.lib = L.load()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.batch = int(batch)
         self.act_dtype = act_dtype
-        self.dt = {torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}[act_dtype]
-        self.np16 = np.uint16
+        self.dt = {torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16, torch.float32: L.DT_F32}[act_dtype]
+        self.f32 = act_dtype == torch.float32
+        self.esz = 4 if self.f32 else 2
+        self.npw = np.float32 if self.f32 else np.uint16      # numpy type of one packed weight
+        self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
+        self.head_only = head_only
         self.spec: NetSpec = build_acr_spec(input_size)
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)
-        self.debug_ref_conv = debug_ref_conv
+        self.debug_ref_conv = debug_ref_conv or self.f32
+        self.run_count = 0          # bumped by every run(): lazily read outputs check it (acr/model.py)
         sd = {k: v.detach().float().cpu().numpy() for k, v in (state_dict or {}).items()
               if v.dtype.is_floating_point}
-        self._build(sd, reuse_memory)
+        self._build(sd, reuse_memory, weights)
 
     # ------------------------------------------------------------------ weights
     def _pack_conv(self, sd, blob: _Blob, wkey: str, bnkey: Optional[str], has_bias: bool, cin_pad: int,
@@ -132,7 +146,7 @@ class Engine:
             cb = None if cb is None else np.tile(cb, 2)
             bn = [None if b is None else np.tile(b, 2) for b in bn]
         cout, cin, k, _ = w.shape
-        wp = np.zeros((cout_pad, k * k, cin_pad), np.uint16)
+        wp = np.zeros((cout_pad, k * k, cin_pad), self.npw)
         bias = np.zeros(cout_pad, np.float32)
         p = lambda a: None if a is None else a.ctypes.data
         L.check(self.lib.acr_b200_pack_conv(p(w), p(cb), p(bn[0]), p(bn[1]), p(bn[2]), p(bn[3]), BN_EPS, cout, cin, k,
@@ -142,7 +156,7 @@ class Engine:
 
     def _pack_raw(self, blob: _Blob, w: np.ndarray, cin_pad: int, cout_pad: int) -> int:
         cout, cin, k, _ = w.shape
-        wp = np.zeros((cout_pad, k * k, cin_pad), np.uint16)
+        wp = np.zeros((cout_pad, k * k, cin_pad), self.npw)
         bias = np.zeros(cout_pad, np.float32)
         w = np.ascontiguousarray(w, np.float32)
         L.check(self.lib.acr_b200_pack_conv(w.ctypes.data, None, None, None, None, None, BN_EPS, cout, cin, k,
@@ -150,10 +164,13 @@ class Engine:
         return blob.add(wp)
 
     # --------------------------------------------------------------------- plan
-    def _build(self, sd, reuse_memory: bool) -> None:
+    def _build(self, sd, reuse_memory: bool, shared_weights: Optional[torch.Tensor] = None) -> None:
         spec, B = self.spec, self.batch
         blob = _Blob()
         ops = spec.ops
+        if self.head_only:   # ACR.head_forward: everything after the trunk; feat32 (channels 0..31 of xcat) is external
+            first = next(i for i, op in enumerate(ops) if op.kind == "coordcat")
+            ops = ops[first:]
 
         # ---- memory geometry of every tensor
         geo: Dict[str, dict] = {}
@@ -166,7 +183,7 @@ class Engine:
                 elif root.dtype == "f32":
                     g = dict(stride=_rup(root.C, 16), esz=4, dt=L.DT_F32)
                 else:
-                    g = dict(stride=_rup(root.C, 16), esz=2, dt=self.dt)
+                    g = dict(stride=_rup(root.C, 16), esz=self.esz, dt=self.dt)
                 g["bytes"] = B * root.H * root.W * g["stride"] * g["esz"]
                 g["offset"] = None
                 geo[root.name] = g
@@ -219,6 +236,10 @@ class Engine:
             for t in r["ins"] + [r["out"]] + r.get("aux", []):
                 last_use[(t.base or t).name] = i
         arena = _Arena()
+        if self.head_only:      # the external feature is copied into the coord-concat buffer before the run
+            xcat = spec.tensors["feat32"].base
+            geom(xcat)["offset"] = arena.alloc(geom(xcat)["bytes"])
+            keep_roots.add(xcat.name)
         for i, r in enumerate(recs):
             for t in [r["out"]] + r.get("aux", []):
                 g = geom(t)
@@ -251,7 +272,7 @@ class Engine:
             ct.C, ct.H, ct.W = t.C, t.H, t.W
             ct.pix_stride, ct.dtype, ct.external = g["stride"], g["dt"], int(ext)
             if pair:   # dense 32-channel NHWC seen as (H, W/2, 64): two x-adjacent pixels form one 128-byte row
-                assert t.base is None and g["stride"] == t.C == 32 and t.W % 2 == 0
+                assert t.base is None and g["stride"] == t.C == 32 and t.W % 2 == 0 and not self.f32
                 ct.C, ct.W, ct.pix_stride = 64, t.W // 2, 64
             return ct
 
@@ -259,7 +280,7 @@ class Engine:
             """3x3 stride-1 32->32 convs on dense tensors run as 64->64 convs on the x-paired grid: same
             bytes in memory, but 128-byte operand rows (SWIZZLE_128B) instead of 64-byte ones."""
             a = r.get("attrs", {})
-            if r["kind"] not in (L.OP_CONV, L.OP_CONV_REF) or "fold_side" in a or a.get("k") != 3 or a.get("s") != 1:
+            if self.f32 or r["kind"] not in (L.OP_CONV, L.OP_CONV_REF) or "fold_side" in a or a.get("k") != 3 or a.get("s") != 1:
                 return False
             ts = r["ins"] + [r["out"]]
             return all(t.C == 32 and t.base is None and t.dtype == "act" and t.W % 32 == 0 for t in ts)
@@ -334,12 +355,18 @@ class Engine:
                     o.w_offset[j] = blob.add(f32(k).reshape(-1))
         self.n_ops = len(recs)
         self._cops = cops
-        self.weights = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).to(self.device)
-        self.arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)
-        plan = C.c_void_p()
-        L.check(self.lib.acr_b200_plan_create(cops, len(recs), B, self.arena.data_ptr(), self.arena_bytes,
-                                              self.weights.data_ptr(), self.weights.numel(), self.dt, C.byref(plan)),
-                "plan_create")
+        if shared_weights is not None:     # same dtype / flags => byte-identical blob (packing is deterministic)
+            if shared_weights.numel() != blob.size or shared_weights.device != self.device:
+                raise L.AcrB200Error("Engine: the shared weight blob does not match this plan")
+            self.weights = shared_weights
+        else:
+            self.weights = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).to(self.device)
+        with torch.cuda.device(self.device):
+            self.arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)
+            plan = C.c_void_p()
+            L.check(self.lib.acr_b200_plan_create(cops, len(recs), B, self.arena.data_ptr(), self.arena_bytes,
+                                                  self.weights.data_ptr(), self.weights.numel(), self.dt, C.byref(plan)),
+                    "plan_create")
         self.plan = plan
 
     def __del__(self):
@@ -351,20 +378,46 @@ class Engine:
             pass
 
     # ---------------------------------------------------------------------- run
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
     def run(self, image: torch.Tensor) -> None:
-        """image: uint8 CUDA tensor (B, S, S, 3) RGB.  Asynchronous on the current stream."""
+        """image: uint8 CUDA tensor (B, S, S, 3) RGB on this engine's device.  Asynchronous on that device's
+        current stream.  Outputs (``view`` / ``map_nchw`` / ``parse_inputs``) alias the arena: they are valid
+        until the next ``run`` on this engine."""
+        if self.head_only:
+            raise L.AcrB200Error("Engine.run: this is a heads-only plan, use run_heads(x)")
         if not (image.is_cuda and image.dtype == torch.uint8 and image.is_contiguous()):
             raise L.AcrB200Error("Engine.run expects a contiguous uint8 CUDA tensor (B,H,W,3)")
+        if image.device != self.device:
+            raise L.AcrB200Error(f"Engine.run: image lives on {image.device}, the plan on {self.device}")
         if tuple(image.shape) != (self.batch, self.input_size, self.input_size, 3):
             raise L.AcrB200Error(f"Engine.run: expected {(self.batch, self.input_size, self.input_size, 3)}, got {tuple(image.shape)}")
-        L.check(self.lib.acr_b200_plan_run(self.plan, image.data_ptr(), L.current_stream()), "plan_run")
+        with torch.cuda.device(self.device):
+            self.run_count += 1
+            L.check(self.lib.acr_b200_plan_run(self.plan, image.data_ptr(), self._stream()), "plan_run")
+
+    def run_heads(self, x: torch.Tensor) -> None:
+        """x: (B,32,S/4,S/4) backbone feature (any float dtype, NCHW like the reference's head_forward input).
+        Copied (and rounded to the storage type) into channels 0..31 of the coord-concat buffer, then the
+        heads-only plan runs."""
+        if not self.head_only:
+            raise L.AcrB200Error("Engine.run_heads needs an engine built with head_only=True")
+        F = self.input_size // 4
+        if tuple(x.shape) != (self.batch, 32, F, F) or not x.is_cuda or x.device != self.device:
+            raise L.AcrB200Error(f"Engine.run_heads: expected a CUDA tensor {(self.batch, 32, F, F)} on {self.device}")
+        with torch.cuda.device(self.device):
+            self.run_count += 1
+            self.view("feat32")[..., :32].copy_(x.permute(0, 2, 3, 1))
+            L.check(self.lib.acr_b200_plan_run(self.plan, None, self._stream()), "plan_run")
 
     def profile(self, image: torch.Tensor) -> Dict[int, Tuple[float, int]]:
         """One serialised, event-bracketed pass: {op kind: (device ms, launches)}."""
         ms = np.zeros(16, np.float32)
         cnt = np.zeros(16, np.int32)
-        L.check(self.lib.acr_b200_plan_profile(self.plan, image.data_ptr(), L.current_stream(), ms.ctypes.data,
-                                               cnt.ctypes.data), "plan_profile")
+        with torch.cuda.device(self.device):
+            L.check(self.lib.acr_b200_plan_profile(self.plan, image.data_ptr(), self._stream(), ms.ctypes.data,
+                                                   cnt.ctypes.data), "plan_profile")
         return {k: (float(ms[k]), int(cnt[k])) for k in range(16) if cnt[k]}
 
     @property
@@ -372,20 +425,24 @@ class Engine:
         return int(self.lib.acr_b200_plan_num_launches(self.plan))
 
     # ------------------------------------------------------------------ outputs
-    def view(self, name: str) -> torch.Tensor:
-        """NHWC view (B,H,W,pix_stride) of a named tensor inside the arena (no copy)."""
-        t = self.spec.tensors[name]
+    def view(self, name) -> torch.Tensor:
+        """NHWC view of a tensor (name or netspec.Tensor) inside the arena, no copy: (B,H,W,stride - c_off)
+        starting at the tensor's first channel (channel slices of a wider buffer start at their c_off)."""
+        t = self.spec.tensors[name] if isinstance(name, str) else name
         g = self.geo[(t.base or t).name]
+        if g["offset"] is None:
+            raise L.AcrB200Error(f"tensor {t.name} is not part of this plan")
         tdt = {L.DT_F32: torch.float32, L.DT_BF16: torch.bfloat16, L.DT_F16: torch.float16}[g["dt"]]
         n = self.batch * t.H * t.W * g["stride"]
         off = g["offset"]
         flat = self.arena[off: off + n * g["esz"]].view(tdt)
-        return flat.view(self.batch, t.H, t.W, g["stride"])
+        v = flat.view(self.batch, t.H, t.W, g["stride"])
+        return v[..., t.c_off:] if t.base is not None and t.c_off else v
 
-    def map_nchw(self, name: str) -> torch.Tensor:
-        """fp32 NCHW copy of an output map with its logical channel count (the reference's layout)."""
-        t = self.spec.tensors[name]
-        return self.view(name)[..., : t.C].permute(0, 3, 1, 2).float().contiguous()
+    def map_nchw(self, name) -> torch.Tensor:
+        """fp32 NCHW copy of a tensor with its logical channel count (the reference's layout)."""
+        t = self.spec.tensors[name] if isinstance(name, str) else name
+        return self.view(t)[..., : t.C].permute(0, 3, 1, 2).float().contiguous()
 
     def parse_inputs(self) -> Dict[str, tuple]:
         out = {}

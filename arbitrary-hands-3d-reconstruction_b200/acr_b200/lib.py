@@ -105,12 +105,31 @@ def ptr(t) -> Optional[int]:
     return t.ctypes.data
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
-def require_cuda(*tensors) -> None:
+def require_cuda(*tensors):
+    """All non-None arguments must be CUDA tensors on ONE device; returns that device (None if no tensor).
+    The kernels are launched on that device's current stream, under a device guard (`on(dev)`), so ops on
+    tensors of a non-current device do not end up on the wrong device / stream."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise AcrB200Error("acr_b200 kernels need CUDA tensors; there is no CPU fallback on the product path")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise AcrB200Error(f"acr_b200: arguments live on different devices ({dev} and {t.device})")
+    return dev
+
+
+def on(device):
+    """Context manager: make `device` current for the launches inside (cudaFuncSetAttribute, events and the
+    launch itself are per device)."""
+    import torch
+    return torch.cuda.device(device)

@@ -33,9 +33,8 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
                  want_camed: bool = True, peers=None):
     """-> dict(verts, joints, center[, verts_camed, pj2d, pj2d_org]); all (n, ...) fp32 CUDA tensors.
     ``peers`` (acr_b200.dist.PeerVertexGather) fuses the cross-GPU vertex all-gather into the kernel."""
-    L.require_cuda(poses, betas, hand_type, cam, offsets, n_dev)
+    dev = L.require_cuda(poses, betas, hand_type, cam, offsets, n_dev, model_l, model_r)
     n = poses.shape[0]
-    dev = poses.device
     poses = poses.contiguous().float()
     betas = betas.contiguous().float()
     out = dict(verts=torch.empty(n, 778, 3, device=dev), joints=torch.empty(n, 21, 3, device=dev),
@@ -58,14 +57,16 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
               L.ptr(cam), L.ptr(offsets), L.ptr(out["verts"]), L.ptr(out["joints"]),
               L.ptr(out["center"]), L.ptr(out.get("verts_camed")), L.ptr(out.get("pj2d")),
               L.ptr(out.get("pj2d_org")))
-    if peers is None:
-        rc = lib.acr_b200_mano_forward(*common, L.current_stream())
-    else:
-        assert n <= peers.rows, "gather buffer too small"
-        import ctypes as C
-        arr = (C.c_uint64 * len(peers.peer_ptrs))(*peers.peer_ptrs)
-        rc = lib.acr_b200_mano_forward_gather(*common, C.cast(arr, C.c_void_p), len(peers.peer_ptrs),
-                                              int(peers.multicast_ptr), int(peers.dst_row_offset), L.current_stream())
+    with L.on(dev):
+        if peers is None:
+            rc = lib.acr_b200_mano_forward(*common, L.current_stream(dev))
+        else:
+            assert n <= peers.rows, "gather buffer too small"
+            import ctypes as C
+            ptrs, mc = peers.launch_targets()
+            arr = (C.c_uint64 * len(ptrs))(*ptrs)
+            rc = lib.acr_b200_mano_forward_gather(*common, C.cast(arr, C.c_void_p), len(ptrs), int(mc),
+                                                  int(peers.dst_row_offset), L.current_stream(dev))
     L.check(rc, "mano_forward")
     return out
 
@@ -73,13 +74,14 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
 def cam_trans(j3d: torch.Tensor, pj2d: torch.Tensor, focal_length: float = 1265.0, img_size: float = 512.0,
               n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(n,21,3), (n,21,2) -> (n,3) camera translation (closed-form least squares on the device)."""
-    L.require_cuda(j3d, pj2d, n_dev)
+    dev = L.require_cuda(j3d, pj2d, n_dev)
     n = j3d.shape[0]
     out = torch.empty(n, 3, device=j3d.device)
     if n:
-        L.check(L.load().acr_b200_cam_trans(L.ptr(j3d.contiguous().float()), L.ptr(pj2d.contiguous().float()),
-                                            L.ptr(n_dev), n, float(focal_length), float(img_size), L.ptr(out),
-                                            L.current_stream()), "cam_trans")
+        with L.on(dev):
+            L.check(L.load().acr_b200_cam_trans(L.ptr(j3d.contiguous().float()), L.ptr(pj2d.contiguous().float()),
+                                                L.ptr(n_dev), n, float(focal_length), float(img_size), L.ptr(out),
+                                                L.current_stream(dev)), "cam_trans")
     return out
 
 
@@ -98,33 +100,36 @@ def one_euro_smooth(poses: torch.Tensor, betas: torch.Tensor, state: OneEuroStat
                     n_dev: Optional[torch.Tensor] = None) -> None:
     """In-place temporal smoothing of (n,48) poses and (n,10) betas (drop-in for acr.utils.smooth_results
     applied per hand as in acr/main.py:69-83)."""
-    L.require_cuda(poses, betas, hand_type, detection_flag, n_dev)
+    dev = L.require_cuda(poses, betas, hand_type, detection_flag, n_dev, state.state)
     assert poses.is_contiguous() and betas.is_contiguous() and poses.dtype == betas.dtype == torch.float32
     if poses.shape[0]:
-        L.check(L.load().acr_b200_one_euro_smooth(L.ptr(poses), L.ptr(betas), L.ptr(hand_type), L.ptr(detection_flag),
-                                                  L.ptr(n_dev), poses.shape[0], L.ptr(state.state), float(smooth_coeff),
-                                                  L.current_stream()), "one_euro_smooth")
+        with L.on(dev):
+            L.check(L.load().acr_b200_one_euro_smooth(L.ptr(poses), L.ptr(betas), L.ptr(hand_type), L.ptr(detection_flag),
+                                                      L.ptr(n_dev), poses.shape[0], L.ptr(state.state), float(smooth_coeff),
+                                                      L.current_stream(dev)), "one_euro_smooth")
 
 
 # ------------------------------------------------------------------------------ rotations
 def rot6d_to_aa(rot6d: torch.Tensor) -> torch.Tensor:
     """(N, 6*J) -> (N, 3*J); drop-in for acr.utils.rot6D_to_angular."""
-    L.require_cuda(rot6d)
+    dev = L.require_cuda(rot6d)
     x = rot6d.contiguous().float()
     nrot = x.numel() // 6
     out = torch.empty(x.shape[0], x.shape[1] // 2, device=x.device)
     if nrot:
-        L.check(L.load().acr_b200_rot6d_to_aa(L.ptr(x), nrot, L.ptr(out), L.current_stream()), "rot6d_to_aa")
+        with L.on(dev):
+            L.check(L.load().acr_b200_rot6d_to_aa(L.ptr(x), nrot, L.ptr(out), L.current_stream(dev)), "rot6d_to_aa")
     return out
 
 
 def rodrigues(aa: torch.Tensor) -> torch.Tensor:
     """(M,3) -> (M,9); drop-in for mano.manolayer.batch_rodrigues."""
-    L.require_cuda(aa)
+    dev = L.require_cuda(aa)
     x = aa.contiguous().float()
     out = torch.empty(x.shape[0], 9, device=x.device)
     if x.shape[0]:
-        L.check(L.load().acr_b200_rodrigues(L.ptr(x), x.shape[0], L.ptr(out), L.current_stream()), "rodrigues")
+        with L.on(dev):
+            L.check(L.load().acr_b200_rodrigues(L.ptr(x), x.shape[0], L.ptr(out), L.current_stream(dev)), "rodrigues")
     return out
 
 
@@ -158,9 +163,9 @@ def parse_maps(maps: Dict[str, tuple], B: int, bufs: ParseBuffers, meta_batch_id
     Fills ``bufs`` asynchronously on the current stream (no host sync)."""
     lib = L.load()
     ms = []
+    dev = L.require_cuda(bufs.counts, *[maps[k][0] for k in maps])
     for k in ("l_center", "r_center", "l_params", "r_params", "l_prior", "r_prior"):
         t, stride = maps[k]
-        L.require_cuda(t)
         assert t.dtype == torch.float32
         m = L.Map()
         m.ptr, m.pix_stride = t.data_ptr(), int(stride)
@@ -169,8 +174,9 @@ def parse_maps(maps: Dict[str, tuple], B: int, bufs: ParseBuffers, meta_batch_id
         meta_batch_ids = meta_batch_ids.to(device=bufs.counts.device, dtype=torch.int64).contiguous()
     if offsets is not None:
         offsets = offsets.to(device=bufs.counts.device, dtype=torch.float32).contiguous()
-    rc = lib.acr_b200_parse(*ms, B, float(conf_thresh), L.ptr(meta_batch_ids), L.ptr(offsets), bufs.struct(),
-                            L.current_stream())
+    with L.on(dev):
+        rc = lib.acr_b200_parse(*ms, B, float(conf_thresh), L.ptr(meta_batch_ids), L.ptr(offsets), bufs.struct(),
+                                L.current_stream(dev))
     L.check(rc, "parse")
     # keep the inputs alive until the kernels have run
     bufs._keep = (meta_batch_ids, offsets, [m for m in maps.values()])

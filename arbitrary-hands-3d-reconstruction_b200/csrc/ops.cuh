@@ -51,6 +51,13 @@ struct PartHeadArgs {
   int batch;
 };
 int launch_parthead(const PartHeadArgs& a, cudaStream_t st);
+// fp32-storage validation plan (validate_f32.cu): same ops, fp32 tensors, fp64 accumulation
+int launch_stem_f32(const TensorRef& img, const TensorRef& out, const float* w, const float* bias, int batch, cudaStream_t st);
+int launch_conv_f32(const ConvArgs& a, cudaStream_t st);
+int launch_fuse_f32(const FuseArgs& a, cudaStream_t st);
+int launch_bilinear2x_f32(const TensorRef& in, const TensorRef& out, int batch, cudaStream_t st);
+int launch_coord_f32(const TensorRef& out, int c_off, int batch, cudaStream_t st);
+int launch_pool_f32(const TensorRef& feat, const TensorRef& logits, float* part, int batch, cudaStream_t st);
 // tcgen05 implicit-GEMM conv (conv_tc.cu)
 struct ConvTcPlan;   // holds the TMA tensor maps of one conv op
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out);

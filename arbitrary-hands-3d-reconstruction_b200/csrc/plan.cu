@@ -48,8 +48,46 @@ static int make_conv_args(const acr_b200_op& op, int batch, char* arena, const c
   return ACR_B200_OK;
 }
 
+// fp32 validation plan: every op on the fp32-storage / fp64-accumulate kernels of validate_f32.cu
+static int run_one_f32(const acr_b200_op& op, int batch, char* arena, const char* weights, const char* external,
+                       cudaStream_t st) {
+  switch (op.kind) {
+    case ACR_OP_STEM:
+      ACR_CHECK_ARG(external != nullptr, "stem: external image pointer is null");
+      return launch_stem_f32(resolve(op.in[0], arena, external), resolve(op.out, arena, external),
+                             reinterpret_cast<const float*>(weights + op.w_offset[0]),
+                             reinterpret_cast<const float*>(weights + op.w_offset[1]), batch, st);
+    case ACR_OP_CONV:
+    case ACR_OP_CONV_REF: {
+      ConvArgs a;
+      int rc = make_conv_args(op, batch, arena, weights, external, &a);
+      if (rc) return rc;
+      return launch_conv_f32(a, st);
+    }
+    case ACR_OP_FUSE: {
+      FuseArgs f;
+      f.out = resolve(op.out, arena, external);
+      f.n_in = op.n_in; f.relu = op.relu; f.batch = batch;
+      ACR_CHECK_ARG(op.n_in >= 1 && op.n_in <= 4, "fuse: n_in");
+      for (int i = 0; i < op.n_in; ++i) { f.in[i] = resolve(op.in[i], arena, external); f.shift[i] = op.shift[i]; }
+      return launch_fuse_f32(f, st);
+    }
+    case ACR_OP_BILINEAR2X:
+      return launch_bilinear2x_f32(resolve(op.in[0], arena, external), resolve(op.out, arena, external), batch, st);
+    case ACR_OP_COORD:
+      return launch_coord_f32(resolve(op.out, arena, external), op.in[0].C, batch, st);
+    case ACR_OP_POOL:
+      return launch_pool_f32(resolve(op.in[0], arena, external), resolve(op.in[1], arena, external),
+                             reinterpret_cast<float*>(arena + op.out.offset), batch, st);
+    default:
+      set_error("op kind %d has no fp32 validation kernel", op.kind);
+      return ACR_B200_EINVAL;
+  }
+}
+
 static int run_one(const acr_b200_op& op, int batch, char* arena, const char* weights, const char* external,
                    int act_dtype, const ConvTcPlan* tc, cudaStream_t st) {
+  if (act_dtype == ACR_DT_F32 && op.kind != ACR_OP_PARTHEAD) return run_one_f32(op, batch, arena, weights, external, st);
   switch (op.kind) {
     case ACR_OP_STEM: {
       ACR_CHECK_ARG(external != nullptr, "stem: external image pointer is null");
@@ -136,7 +174,8 @@ extern "C" int acr_b200_plan_create(const acr_b200_op* ops, int n_ops, int batch
                                     size_t arena_bytes, const void* weights, size_t weight_bytes,
                                     int act_dtype, acr_b200_plan** plan_out) {
   ACR_CHECK_ARG(ops && n_ops > 0 && batch > 0 && arena && weights && plan_out, "plan_create: bad arguments");
-  ACR_CHECK_ARG(act_dtype == ACR_DT_BF16 || act_dtype == ACR_DT_F16, "plan_create: act_dtype must be bf16/f16");
+  ACR_CHECK_ARG(act_dtype == ACR_DT_BF16 || act_dtype == ACR_DT_F16 || act_dtype == ACR_DT_F32,
+                "plan_create: act_dtype must be bf16/f16 (product) or f32 (validation plan)");
   acr_b200_plan* p = new (std::nothrow) acr_b200_plan();
   ACR_CHECK_ARG(p != nullptr, "plan_create: out of host memory");
   p->ops.assign(ops, ops + n_ops);
@@ -155,7 +194,7 @@ extern "C" int acr_b200_plan_create(const acr_b200_op* ops, int n_ops, int batch
       const size_t need = op.out.offset + (size_t)batch * op.out.H * op.out.W * op.out.pix_stride * esz;
       if (need > arena_bytes) { set_error("op %d: output exceeds the arena (%zu > %zu)", i, need, arena_bytes); rc = ACR_B200_EINVAL; break; }
     }
-    if (op.kind == ACR_OP_CONV) {
+    if (op.kind == ACR_OP_CONV && act_dtype != ACR_DT_F32) {
       ConvArgs a;
       rc = make_conv_args(op, batch, p->arena, p->weights, nullptr, &a);
       if (rc == ACR_B200_OK) rc = conv_tc_prepare(a, act_dtype, &p->tc[i]);
@@ -177,7 +216,7 @@ extern "C" int acr_b200_plan_create(const acr_b200_op* ops, int n_ops, int batch
 }
 
 extern "C" int acr_b200_plan_run(acr_b200_plan* p, const void* image, void* stream) {
-  ACR_CHECK_ARG(p && image, "plan_run: bad arguments");
+  ACR_CHECK_ARG(p != nullptr, "plan_run: bad arguments");   // image may be NULL for a heads-only plan (no external op)
   cudaStream_t main_st = static_cast<cudaStream_t>(stream);
   const int n = (int)p->ops.size();
   if (p->n_streams == 1) {

@@ -18,6 +18,18 @@ Reference functions restated (in /root/reference/acr/model.py):
 conv/fuse output to that storage type, which is where the B200 path rounds; the
 arithmetic itself stays fp32.  With ``act_dtype=None`` this is the reference's
 fp32 path.
+
+``fold_round=True`` (needs ``act_dtype``) additionally restates the ROUNDING POINTS of
+the 16-bit product path -- not its kernels: eval-mode BatchNorm is folded into the conv
+weights and the folded weights are rounded to the storage type (bias stays fp32), the
+normalised stem input is rounded (the im2col taps are stored 16-bit), the raw params /
+cam head outputs are rounded (they are stored 16-bit before the final 1x1 conv), the
+softmax weights of the attention pooling are rounded, and contact_layers[4|5] is
+evaluated in its algebraically folded form (one 128->109 1x1 conv on the stored
+[params106 | cam3] tensor with rounded weights + a per-image fp32 bias).  The result is
+what an exact-arithmetic machine with the product path's storage types would produce:
+the whole-network bf16 comparison against it isolates wiring errors from storage
+round-off (tests/test_gpu_network.py).
 """
 import torch
 import torch.nn.functional as Fn
@@ -27,9 +39,11 @@ WIDTHS = (32, 64, 128, 256)
 
 
 class _Net:
-    def __init__(self, sd, act_dtype=None):
+    def __init__(self, sd, act_dtype=None, fold_round=False):
         self.sd = sd
         self.q = act_dtype
+        self.fold = bool(fold_round)
+        assert not (self.fold and act_dtype is None), "fold_round needs a storage dtype"
 
     # -- helpers ------------------------------------------------------------
     def rnd(self, x):
@@ -48,20 +62,39 @@ class _Net:
         s = g / torch.sqrt(v + EPS)
         return x * s.view(1, -1, 1, 1) + (b - m * s).view(1, -1, 1, 1)
 
+    def convbn(self, x, ckey, bkey=None, stride=1):
+        """conv (+bias) (+eval BatchNorm).  fold mode: y = conv(x, rnd(w * s)) + (beta - mean*s + cb*s), the
+        weight/bias split of acr_b200_pack_conv."""
+        if not self.fold:
+            y = self.conv(x, ckey, stride)
+            return self.bn(y, bkey) if bkey else y
+        w = self.sd[ckey + ".weight"].float()
+        cb = self.sd.get(ckey + ".bias")
+        if bkey:
+            g, b = self.sd[bkey + ".weight"].float(), self.sd[bkey + ".bias"].float()
+            m, v = self.sd[bkey + ".running_mean"].float(), self.sd[bkey + ".running_var"].float()
+            sc = g / torch.sqrt(v + EPS)
+            sh = b - m * sc
+        else:
+            sc, sh = torch.ones(w.shape[0]), torch.zeros(w.shape[0])
+        if cb is not None:
+            sh = sh + cb.float() * sc
+        return Fn.conv2d(x, self.rnd(w * sc.view(-1, 1, 1, 1)), sh, stride, w.shape[-1] // 2)
+
     def cbr(self, x, ckey, bkey, stride=1, relu=True):
-        y = self.bn(self.conv(x, ckey, stride), bkey)
+        y = self.convbn(x, ckey, bkey, stride)
         return self.rnd(torch.relu(y) if relu else y)
 
     def basic(self, x, p):
         y = self.cbr(x, p + ".conv1", p + ".bn1")
-        y = self.bn(self.conv(y, p + ".conv2"), p + ".bn2") + x
+        y = self.convbn(y, p + ".conv2", p + ".bn2") + x
         return self.rnd(torch.relu(y))
 
     def bottleneck(self, x, p, down):
         res = self.cbr(x, p + ".downsample.0", p + ".downsample.1", relu=False) if down else x
         y = self.cbr(x, p + ".conv1", p + ".bn1")
         y = self.cbr(y, p + ".conv2", p + ".bn2")
-        y = self.bn(self.conv(y, p + ".conv3"), p + ".bn3") + res
+        y = self.convbn(y, p + ".conv3", p + ".bn3") + res
         return self.rnd(torch.relu(y))
 
     def hr_module(self, xs, prefix, multi):
@@ -93,6 +126,8 @@ class _Net:
     def backbone(self, image_bhwc):
         x = image_bhwc.float().permute(0, 3, 1, 2)
         x = (x / 255.0) * 2.0 - 1.0
+        if self.fold:
+            x = self.rnd(x)          # the im2col taps of the tensor-core stem are stored in the 16-bit type
         x = self.cbr(x, "backbone.conv1", "backbone.bn1", stride=2)
         x = self.cbr(x, "backbone.conv2", "backbone.bn2", stride=2)
         for i in range(4):
@@ -115,13 +150,13 @@ class _Net:
         y = self.cbr(y, p + ".3", p + ".4")
         p = "backbone.hand_segm.segm_head.segm_net.double_conv"
         y = self.cbr(y, p + ".0", p + ".1")
-        return self.rnd(self.conv(y, p + ".3"))
+        return self.rnd(self.convbn(y, p + ".3"))
 
     def head_stack(self, x, p):
         y = self.cbr(x, p + ".0.0", p + ".0.1", stride=2)
         for k in range(2):
             y = self.basic(y, f"{p}.1.{k}.0")
-        return self.conv(y, p + ".2")
+        return self.convbn(y, p + ".2")
 
     def heads(self, x):
         B, _, H, W = x.shape
@@ -137,12 +172,19 @@ class _Net:
             cam = self.head_stack(xc, f"{s}_final_layers.3")
             out[f"{s}_prior_maps"] = self.head_stack(xc, f"{s}_final_layers.4")
             cam = torch.cat([torch.pow(1.1, cam[:, :1]), cam[:, 1:]], 1)
+            if self.fold:            # both heads are stored 16-bit (slices of the 128-channel input of the folded conv)
+                cam, prm = self.rnd(cam), self.rnd(prm)
             raw[s] = torch.cat([cam, prm], 1)                      # (B,109,64,64)
         # ---- part branch
         att = seg[:, 1:, ::2, ::2]                                 # nearest 1/2, drop background
         contact = self.cbr(xc, "contact_layers.1.0", "contact_layers.1.1")
         shape_f = self.conv(contact, "cam_shape_layers.1.0")
-        a = torch.softmax(att.reshape(B, 32, -1), -1)
+        if self.fold:                # split softmax with weights rounded to the storage type; they still sum to one
+            lg = att.reshape(B, 32, -1)
+            e = self.rnd(torch.exp(lg - lg.max(-1, keepdim=True).values))
+            a = e / e.sum(-1, keepdim=True)
+        else:
+            a = torch.softmax(att.reshape(B, 32, -1), -1)
         wc = torch.matmul(a, contact.reshape(B, 256, -1).transpose(1, 2)).transpose(1, 2)   # (B,256,32)
         ws = torch.matmul(a, shape_f.reshape(B, 64, -1).transpose(1, 2)).transpose(1, 2)    # (B,64,32)
         for s, sl, li, ci in (("l", slice(16, 32), 2, 4), ("r", slice(0, 16), 3, 5)):
@@ -152,6 +194,16 @@ class _Net:
             sh = Fn.linear(ws[:, :, sl].reshape(B, -1), self.sd[f"cam_shape_layers.{li}.weight"].float(),
                            self.sd[f"cam_shape_layers.{li}.bias"].float())
             pare = torch.cat([off, sh], 1)[:, :, None, None].expand(-1, -1, 64, 64)
+            if self.fold:
+                # out = W[:, :109].pm + W[:, 109:112].pm[:3] + (b + W[:, 112:].pare),  pm = [cam3 | params106]
+                Wf = self.sd[f"contact_layers.{ci}.weight"].float().reshape(109, 218)
+                bf = self.sd[f"contact_layers.{ci}.bias"].float()
+                w_prm, w_cam = self.rnd(Wf[:, 3:109]), self.rnd(Wf[:, 0:3] + Wf[:, 109:112])
+                bias_img = bf[None] + torch.cat([off, sh], 1) @ Wf[:, 112:].t()            # (B,109) fp32
+                out[f"{s}_params_maps"] = (torch.einsum("oc,bchw->bohw", w_prm, raw[s][:, 3:])
+                                           + torch.einsum("oc,bchw->bohw", w_cam, raw[s][:, :3])
+                                           + bias_img[:, :, None, None])
+                continue
             inp = torch.cat([raw[s], raw[s][:, :3], pare], 1)                               # (B,218,64,64)
             out[f"{s}_params_maps"] = self.conv(inp, f"contact_layers.{ci}")
         out["segms"] = seg
@@ -159,10 +211,16 @@ class _Net:
         return out
 
 
-def net_forward(sd, image_bhwc, act_dtype=None, return_backbone=False):
+def head_forward(sd, x, act_dtype=None, fold_round=False):
+    """ACR.head_forward (acr/model.py:47-65): backbone feature (B,32,128,128) -> the 7 maps."""
+    with torch.no_grad():
+        return _Net(sd, act_dtype, fold_round).heads(x.float())
+
+
+def net_forward(sd, image_bhwc, act_dtype=None, return_backbone=False, fold_round=False):
     """image uint8/float (B,512,512,3) RGB 0..255 -> the 7 maps of ACR.head_forward."""
     with torch.no_grad():
-        n = _Net(sd, act_dtype)
+        n = _Net(sd, act_dtype, fold_round)
         x = n.backbone(image_bhwc)
         out = n.heads(x)
         if return_backbone:

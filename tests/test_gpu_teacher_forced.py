@@ -1,0 +1,125 @@
+"""GPU parity, teacher forced: EVERY launch of the network plan is compared with the oracle's restatement of
+that op (oracle/op_ref.py, unrounded fp32 parameters) applied to the plan's OWN stored inputs.  No error
+accumulates from op to op and the seeded random network cannot amplify storage round-off, so the bound is
+the per-op one: storage rounding of weights and of the one output (2^-7 of the op's output range for bf16,
+2^-10 for fp16, 2e-5 for the fp32 validation plan).  This pins fuse layers, bilinear up-sampling, coord
+channels, every head stack, the attention pooling, the part head and the folded final conv individually --
+a wrong align_corners, BN eps, coord formula, tap order or weight key shows up as an O(1) error of ONE op."""
+import os
+
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10, torch.float32: 2e-5}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from acr_b200.synth import load_bn_calibration, synth_state_dict
+    return synth_state_dict(0, bn_stats=load_bn_calibration(0))
+
+
+@pytest.fixture(scope="module")
+def image():
+    gi = torch.Generator().manual_seed(123)
+    return torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+
+
+def sweep(eng, sd, image, tol):
+    """-> list of (op index, description, rel err); asserts nothing."""
+    from acr_b200 import lib as L
+    from oracle import op_ref
+    sdf = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
+    get = lambda t: eng.map_nchw(t).cpu()
+    rows = []
+    pool_in = None
+    for i, r in enumerate(eng.recs):
+        kind, a = r["kind"], r.get("attrs", {})
+        checks = []      # (label, got, expected)
+        if kind in (L.OP_CONV, L.OP_CONV_REF):
+            if "stem" in a:
+                checks.append(("stem 27->64 1x1 on im2col", get(r["out"]), op_ref.stem_from_cols(get(r["ins"][0])[:, :27], sdf)))
+            elif "fold_side" in a:
+                s = a["fold_side"]
+                raw = eng.view(r["ins"][0]).float().cpu()                      # (B,64,64,128): params 0..105, cam 112..114
+                prm, cam = raw[..., :106].permute(0, 3, 1, 2), raw[..., 112:115].permute(0, 3, 1, 2)
+                pare = eng.view(f"{s}_pare").float().cpu().reshape(raw.shape[0], -1)[:, :106]
+                checks.append((f"contact_layers[{'4' if s == 'l' else '5'}] folded 218->109", get(r["out"]),
+                               op_ref.final_params(prm, cam, pare, sdf, s)))
+            else:
+                res = get(r["ins"][1]) if a["residual"] else None
+                exp = op_ref.conv_bn_act(get(r["ins"][0]), sdf, a["w"], a["bn"], a["s"], a["relu"], res, a["pow11"])
+                checks.append((f"conv {a['w']} k{a['k']} s{a['s']}", get(r["out"]), exp))
+        elif kind == L.OP_STEM:
+            checks.append(("stem (CUDA-core form)", get(r["out"]), op_ref.stem(image, sdf)))
+        elif kind == L.OP_IM2COL_STEM:
+            checks.append(("im2col of the normalised frame", get(r["out"])[:, :27], op_ref.im2col_stem(image)))
+        elif kind == L.OP_FUSE:
+            checks.append((f"fuse x{len(r['ins'])}", get(r["out"]), op_ref.fuse([get(t) for t in r["ins"]], a["shifts"], a["relu"])))
+        elif kind == L.OP_BILINEAR2X:
+            checks.append(("bilinear x2", get(r["out"]), op_ref.bilinear2x(get(r["ins"][0]))))
+        elif kind == L.OP_COORD:
+            xc = eng.view(r["out"]).float().cpu()
+            exp = op_ref.coord(xc.shape[1], xc.shape[2])[None].expand(xc.shape[0], -1, -1, -1)
+            checks.append(("coord channels", xc[..., 32:34].permute(0, 3, 1, 2), exp))
+            assert float(xc[..., 34:].abs().max()) == 0.0, "pad channels of the coord concat are not zero"
+        elif kind == L.OP_POOL:
+            pool_in = r["ins"]                                                  # partials are checked after the merge
+        elif kind == L.OP_PARTHEAD:
+            B = eng.batch
+            pooled = eng.view("pooled").float().cpu().view(B, 256, 32)
+            checks.append(("attention pooling (softmax over HW x features)", pooled,
+                           op_ref.attention_pool(get(pool_in[0]), get(pool_in[1]))))
+            for s in "lr":
+                pare = eng.view(f"{s}_pare").float().cpu().reshape(B, -1)[:, :106]
+                checks.append((f"part head {s}: LocallyConnected2d + Linear", pare, op_ref.part_offsets(pooled, sdf, s)))
+        else:
+            raise AssertionError(f"op kind {kind} has no teacher-forced check")
+        for label, got, exp in checks:
+            assert torch.isfinite(got).all(), (i, label)
+            rows.append((i, label, rel_err(got.numpy(), exp.numpy())))
+    return rows
+
+
+def _run(sd, image, dtype):
+    from acr_b200.engine import Engine
+    torch.set_num_threads(os.cpu_count())
+    eng = Engine(sd, image.shape[0], "cuda", dtype, reuse_memory=False)   # every intermediate tensor is kept
+    eng.run(image.cuda())
+    torch.cuda.synchronize()
+    rows = sweep(eng, sd, image, TOL[dtype])
+    worst = sorted(rows, key=lambda r: -r[2])[:5]
+    print(f"teacher-forced sweep {dtype}: {len(rows)} checks over {len(eng.recs)} launches; worst:",
+          [(i, l, f"{e:.2e}") for i, l, e in worst])
+    assert len(rows) >= len(eng.recs) - 1
+    bad = [(i, l, e) for i, l, e in rows if not e <= TOL[dtype]]
+    assert not bad, f"{len(bad)} ops above {TOL[dtype]:.2e}: {bad[:8]}"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_every_op_teacher_forced_16bit(sd, image, dtype):
+    """The product plans (tcgen05 conv, x-paired 32-channel convs, tensor-core stem and pooling)."""
+    _run(sd, image, dtype)
+
+
+def test_every_op_teacher_forced_fp32_validation_plan(sd, image):
+    """The fp32 validation plan (model_precision='fp32'): fp32 storage, fp64 accumulate."""
+    _run(sd, image, torch.float32)
+
+
+def test_heads_only_plan_teacher_forced(sd, image):
+    """The ACR.head_forward plan (ops after the trunk) on an external feature."""
+    from acr_b200.engine import Engine
+    from oracle import net_ref
+    torch.set_num_threads(os.cpu_count())
+    x = net_ref._Net(sd).backbone(image[:1])
+    eng = Engine(sd, 1, "cuda", torch.bfloat16, reuse_memory=False, head_only=True)
+    eng.run_heads(x.cuda())
+    torch.cuda.synchronize()
+    rows = sweep(eng, sd, image[:1], TOL[torch.bfloat16])
+    bad = [(i, l, e) for i, l, e in rows if not e <= TOL[torch.bfloat16]]
+    assert len(rows) >= 55 and not bad, bad[:8]
