@@ -60,14 +60,17 @@ class ACR(nn.Module):
     @torch.no_grad()
     def fused_forward(self, images_rgb_u8, offsets, out=None, peers=None):
         """Sync-free pipeline: backbone + heads + parse + MANO enqueued back to back; MANO runs over
-        the worst case 2B rows and skips rows >= L+R on the device.  Returns dense buffers."""
+        the worst case 2B rows and skips rows >= L+R on the device.  Returns dense buffers (zero copy: the
+        parse buffers are shared per batch size, consume them before the next call).  ``peers``
+        (acr_b200.dist.PeerVertexGather): the MANO kernel also stores vertices and row counts into every
+        rank's gather buffer."""
         B = images_rgb_u8.shape[0]
         meta = {'image': images_rgb_u8, 'offsets': offsets, 'batch_ids': None}
         eng, bufs = self.model.forward_dense(meta)
         from acr_b200 import ops as _ops
         ml, mr = self.mano_regression.models()
         mano = _ops.mano_forward(ml, mr, bufs.poses, bufs.betas, bufs.hand_type, 1, self.mano_regression.center_idx,
-                                 bufs.cam, bufs.offsets_out, n_dev=bufs.counts[2:3], peers=peers)
+                                 bufs.cam, bufs.offsets_out, n_dev=bufs.counts[2:3], peers=peers, counts=bufs.counts)
         if args().cam_trans_mode == 'lstsq':
             mano['cam_trans'] = _ops.cam_trans(mano['joints'], mano['pj2d'], args().focal_length, 512.0,
                                                n_dev=bufs.counts[2:3])

@@ -43,21 +43,43 @@ def compact_gathered(gathered: torch.Tensor, counts: torch.Tensor) -> List[torch
 
 
 class PeerVertexGather:
-    """Vertex all-gather fused into the MANO kernel: a symmetric-memory buffer (world, R, 778, 3) whose peer
-    addresses (and, with NVLS, its multicast address) are handed to ``acr_b200_mano_forward_gather``; the
-    kernel's epilogue stores every vertex into all ranks' buffers over NVLink (``multimem.st`` through the
-    NVSwitch when multicast is available, per-peer stores otherwise).  ``finish()`` is the cross-rank barrier
-    that makes the stores of all ranks visible (symmetric-memory signal pads, enqueued on the current stream)."""
+    """Vertex all-gather fused into the MANO kernel (``acr_b200_mano_forward_gather``, protocol in
+    include/acr_b200.h).  One symmetric-memory allocation per rank holds TWO gather slots -- each
+    ``verts (world, rows, 778, 3)`` fp32 + ``counts (world, 8)`` int32 -- and one arrival flag per rank.
+    Launch s writes slot s & 1 of every rank over NVLink (16-byte ``multimem.st`` through the NVLS multicast
+    mapping when there is one, 16-byte peer stores otherwise), row counts included, and its last CTA publishes
+    s in every rank's flag word.  There is no barrier and no NCCL call: the kernel itself waits (on flags in
+    its own memory) until the slot it is about to overwrite has been released, which with two slots is a
+    dependency on the PREVIOUS step of the peers.
+
+    Contract: consume step k's gathered data (``gathered()`` / ``counts()`` after ``finish()``) on the
+    launching stream before the next fused launch -- then no peer can overwrite it while it is read.
+    torch symmetric memory only provides the mapped addresses."""
+
+    NV3 = 778 * 3
 
     def __init__(self, rows: int, device, group=None, use_multicast: bool = True):
+        import ctypes as C
+
         import torch.distributed._symmetric_memory as symm_mem
+
+        from . import lib as L
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.rows = int(rows)
-        self.buf = symm_mem.empty((self.world, self.rows, 778, 3), dtype=torch.float32, device=device)
+        if self.rows % 2 or self.world > 8:
+            raise ValueError("PeerVertexGather: rows per rank must be even and world <= 8")
+        self.device = torch.device(device)
+        verts_bytes = self.world * self.rows * self.NV3 * 4
+        self.counts_offset = (verts_bytes + 15) // 16 * 16
+        self.slot_bytes = (self.counts_offset + self.world * 32 + 255) // 256 * 256
+        self.flags_offset = 2 * self.slot_bytes
+        total = self.flags_offset + 256
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.local_state = torch.zeros(2, dtype=torch.int64, device=self.device)
         mc = 0
         if use_multicast:
             try:
@@ -66,14 +88,39 @@ class PeerVertexGather:
             except Exception:
                 mc = 0
         self.multicast_ptr = mc
-        self.dst_row_offset = self.rank * self.rows
+        d = L.Gather()
+        for r, ptr in enumerate(self.hdl.buffer_ptrs):
+            d.peer_base[r] = int(ptr)
+        d.multicast_base, d.world, d.rank, d.rows = mc, self.world, self.rank, self.rows
+        d.slot_bytes, d.counts_offset, d.flags_offset = self.slot_bytes, self.counts_offset, self.flags_offset
+        d.local_state = self.local_state.data_ptr()
+        self.desc = d
+        self.step = 0            # host mirror of the device step counter (which slot holds the latest data)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)          # every rank's flags are zero before anybody publishes
 
     @property
     def mode(self) -> str:
-        return "multimem.st (NVLS multicast)" if self.multicast_ptr else "peer stores"
+        return "16-byte multimem.st (NVLS multicast)" if self.multicast_ptr else "16-byte peer stores"
+
+    def note_launch(self) -> None:
+        self.step += 1
 
     def finish(self) -> None:
-        self.hdl.barrier(channel=0)
+        """Stream-ordered: returns (on the device) once the latest step of EVERY rank has landed here."""
+        from . import lib as L
+        with L.on(self.device):
+            L.check(L.load().acr_b200_gather_wait(self.desc, L.current_stream(self.device)), "gather_wait")
+
+    def _slot(self) -> torch.Tensor:
+        s = self.step & 1
+        return self.buf[s * self.slot_bytes: (s + 1) * self.slot_bytes]
 
     def gathered(self) -> torch.Tensor:
-        return self.buf
+        """(world, rows, 778, 3) view of the slot written by the latest launch (valid after ``finish()``)."""
+        n = self.world * self.rows * self.NV3
+        return self._slot()[: n * 4].view(torch.float32).view(self.world, self.rows, 778, 3)
+
+    def counts(self) -> torch.Tensor:
+        """(world, 8) int32 row counts of every shard, same slot."""
+        return self._slot()[self.counts_offset: self.counts_offset + self.world * 32].view(torch.int32).view(self.world, 8)

@@ -45,10 +45,17 @@ class Op(C.Structure):
                 ("stream_id", C.c_int32), ("wait_mask", C.c_int32), ("fparam", C.c_float * 4)]
 
 
+class Gather(C.Structure):
+    """acr_b200_gather (include/acr_b200.h): symmetric gather allocation of the fused vertex all-gather."""
+    _fields_ = [("peer_base", C.c_uint64 * 8), ("multicast_base", C.c_uint64), ("world", C.c_int32), ("rank", C.c_int32),
+                ("rows", C.c_int64), ("slot_bytes", C.c_uint64), ("counts_offset", C.c_uint64), ("flags_offset", C.c_uint64),
+                ("local_state", C.c_void_p)]
+
+
 _lib: Optional[C.CDLL] = None
 
 EXPORTS = ["acr_b200_last_error", "acr_b200_version", "acr_b200_mano_model_floats", "acr_b200_mano_pack_model",
-           "acr_b200_mano_forward", "acr_b200_mano_forward_gather", "acr_b200_cam_trans", "acr_b200_preprocess", "acr_b200_one_euro_state_floats", "acr_b200_one_euro_smooth", "acr_b200_rot6d_to_aa", "acr_b200_rodrigues", "acr_b200_parse",
+           "acr_b200_mano_forward", "acr_b200_mano_forward_gather", "acr_b200_gather_wait", "acr_b200_cam_trans", "acr_b200_preprocess", "acr_b200_one_euro_state_floats", "acr_b200_one_euro_smooth", "acr_b200_rot6d_to_aa", "acr_b200_rodrigues", "acr_b200_parse",
            "acr_b200_plan_create", "acr_b200_plan_run", "acr_b200_plan_profile", "acr_b200_plan_num_launches", "acr_b200_plan_destroy",
            "acr_b200_run_op", "acr_b200_pack_conv"]
 
@@ -69,7 +76,8 @@ def load() -> C.CDLL:
     lib.acr_b200_mano_pack_model.argtypes = [vp] * 6 + [i32, vp]
     lib.acr_b200_mano_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.acr_b200_mano_forward_gather.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
-                                                 vp, i32, C.c_uint64, C.c_int64, vp]
+                                                 vp, C.POINTER(Gather), vp]
+    lib.acr_b200_gather_wait.argtypes = [C.POINTER(Gather), vp]
     lib.acr_b200_cam_trans.argtypes = [vp, vp, vp, i32, f32, f32, vp, vp]
     lib.acr_b200_preprocess.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.acr_b200_one_euro_state_floats.restype = C.c_size_t

@@ -30,9 +30,10 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
                  betas: torch.Tensor, hand_type: Optional[torch.Tensor] = None, default_side: int = 1,
                  center_idx: Optional[int] = 9, cam: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
-                 want_camed: bool = True, peers=None):
+                 want_camed: bool = True, peers=None, counts: Optional[torch.Tensor] = None):
     """-> dict(verts, joints, center[, verts_camed, pj2d, pj2d_org]); all (n, ...) fp32 CUDA tensors.
-    ``peers`` (acr_b200.dist.PeerVertexGather) fuses the cross-GPU vertex all-gather into the kernel."""
+    ``peers`` (acr_b200.dist.PeerVertexGather) fuses the cross-GPU vertex all-gather into the kernel; ``counts``
+    (8 int32, acr_b200_parse's row counts) then travels with the vertices."""
     dev = L.require_cuda(poses, betas, hand_type, cam, offsets, n_dev, model_l, model_r)
     n = poses.shape[0]
     poses = poses.contiguous().float()
@@ -63,10 +64,9 @@ def mano_forward(model_l: Optional[torch.Tensor], model_r: Optional[torch.Tensor
         else:
             assert n <= peers.rows, "gather buffer too small"
             import ctypes as C
-            ptrs, mc = peers.launch_targets()
-            arr = (C.c_uint64 * len(ptrs))(*ptrs)
-            rc = lib.acr_b200_mano_forward_gather(*common, C.cast(arr, C.c_void_p), len(ptrs), int(mc),
-                                                  int(peers.dst_row_offset), L.current_stream(dev))
+            rc = lib.acr_b200_mano_forward_gather(*common, L.ptr(counts), C.byref(peers.desc), L.current_stream(dev))
+            if rc == L.OK:
+                peers.note_launch()
     L.check(rc, "mano_forward")
     return out
 

@@ -15,4 +15,4 @@ void set_error(const char* fmt, ...) {
 }  // namespace acr
 
 extern "C" const char* acr_b200_last_error(void) { return acr::g_err; }
-extern "C" const char* acr_b200_version(void) { return "acr_b200 r1 sm_100a"; }
+extern "C" const char* acr_b200_version(void) { return "acr_b200 r2 sm_100a"; }

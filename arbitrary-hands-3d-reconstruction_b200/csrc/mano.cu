@@ -53,17 +53,60 @@ struct ManoParams {
   float* verts_camed;
   float* pj2d;
   float* pj2d_org;
-  // fused vertex all-gather (acr_b200_mano_forward_gather)
-  float* peer_verts[8];
-  float* mc_verts;      // NVLS multicast address of the gather buffer, or nullptr
-  int n_peers;
-  long long dst_row;    // first row of this rank's block inside every gather buffer
+  // fused vertex all-gather (acr_b200_mano_forward_gather, protocol in include/acr_b200.h)
+  int gather;                    // 0 = plain launch
+  char* peer_base[8];            // every rank's symmetric allocation, mapped into this rank's address space
+  char* mc_base;                 // NVLS multicast address of the same allocation, or nullptr (-> per-peer stores)
+  int world, rank;
+  long long dst_row;             // first row of this rank's block inside a slot (= rank * rows, even)
+  unsigned long long slot_bytes, counts_offset, flags_offset;
+  unsigned long long* step_dev;  // device-local: gather launches completed so far
+  unsigned int* done_ctr;        // device-local: CTAs of the running launch that have finished
+  const int32_t* counts_src;     // (8) int32 row counts of this shard (acr_b200_parse), carried along
 };
 
-// one value to every GPU of the multicast group: the NVSwitch replicates the store (NVLS)
+// one value / one 16-byte vector to every GPU of the multicast group: the NVSwitch replicates the store (NVLS)
 __device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void multimem_st_v4(float* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded spin on arrival flags in THIS rank's memory: a peer that never arrives must fail the launch, not hang the box
+__device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, unsigned long long target) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < target) {
+    __nanosleep(200);
+    if (clock64() - t0 > 60000000000ll) {   // ~30 s
+      printf("acr_b200 gather: rank flag %p stuck at %llu < %llu\n", (const void*)flag, ld_acquire_sys(flag), target);
+      __trap();
+    }
+  }
+}
+
+// packed fp32 pairs: Blackwell issues two IEEE fp32 FMAs per FFMA2 instruction (fma.rn.f32x2), which is what
+// lifts the blend-shape loop off the FP32 issue bound (each lane is a plain fmaf: results are bit-identical)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+constexpr int STAGE_ROW = 4 + VPB * 3;   // floats: a hand's 384 vertex floats at the offset that matches their global alignment
 
 struct ProjCtx {  // per-hand projection constants kept in shared memory
   float s, tx, ty, padw, padh, ltx, lty;
@@ -98,11 +141,39 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
   __shared__ float s_ctr[HG][3];
   __shared__ ProjCtx s_pc[HG];
   __shared__ int s_side[HG];
+  __shared__ __align__(16) float s_stage[HG][STAGE_ROW];   // vertices of this CTA, staged for 16-byte stores
+  __shared__ int s_last;
 
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int g0 = blockIdx.x * HG;
-  if (g0 >= n) return;
   const int t = threadIdx.x;
+  // ---- fused all-gather bookkeeping.  This launch is gather step `step + 1`; it writes slot (step + 1) & 1.
+  unsigned long long step = 0;
+  char* slot_mc = nullptr;
+  unsigned long long slot_off = 0;
+  if (p.gather) {
+    step = *p.step_dev;                       // stable during the launch: only the last CTA advances it, at the very end
+    slot_off = ((step + 1) & 1ull) * p.slot_bytes;
+    slot_mc = p.mc_base ? p.mc_base + slot_off : nullptr;
+    // CTA (0,0) carries the 32 bytes of row counts of this shard to every rank (no separate collective)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t < 8 && p.counts_src) {
+      // the slot is free once every peer has signalled step `step` (see below)
+      for (int r = 0; r < p.world; ++r) wait_flag_ge(reinterpret_cast<const unsigned long long*>(p.peer_base[p.rank] + p.flags_offset) + r, step);
+      const int32_t cv = p.counts_src[t];
+      const unsigned long long off = slot_off + p.counts_offset + ((size_t)p.rank * 8 + t) * 4;
+      if (p.mc_base) multimem_st_f32(reinterpret_cast<float*>(p.mc_base + off), __int_as_float(cv));
+      else for (int r = 0; r < p.world; ++r) *reinterpret_cast<int32_t*>(p.peer_base[r] + off) = cv;
+    }
+  }
+  const bool active = g0 < n;
+  if (active && p.gather) {
+    // Slot (step+1)&1 was last written by step-1.  A peer signals step `step` only after its launch `step`, which it
+    // enqueued after consuming step-1's data (the consume-before-next-launch contract) -> once every peer's flag in
+    // OUR memory reads >= step, nobody reads the slot any more.  With two slots this wait is one whole step old.
+    if (t < p.world) wait_flag_ge(reinterpret_cast<const unsigned long long*>(p.peer_base[p.rank] + p.flags_offset) + t, step);
+    __syncthreads();
+  }
+  if (active) {
 
   // ---------------------------------------------------------------- phase 1: rigid transforms
   {
@@ -221,11 +292,11 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
     if (!any) continue;  // block-uniform
     const float* __restrict__ m = p.model[side];
     const float* __restrict__ dirs = m + OFF_DIRS;
-    float acc[HG][3];
+    unsigned long long acc2[HG / 2][3];   // (hand 2i, hand 2i+1) packed: one FFMA2 serves two hands
     {
       const float v0 = m[OFF_VT + 0 * NVP + vc], v1 = m[OFF_VT + 1 * NVP + vc], v2 = m[OFF_VT + 2 * NVP + vc];
 #pragma unroll
-      for (int h = 0; h < HG; ++h) { acc[h][0] = v0; acc[h][1] = v1; acc[h][2] = v2; }
+      for (int h = 0; h < HG / 2; ++h) { acc2[h][0] = pk2(v0, v0); acc2[h][1] = pk2(v1, v1); acc2[h][2] = pk2(v2, v2); }
     }
     // shape rows first (v_shaped), then pose rows, like the reference's evaluation order
 #pragma unroll 5
@@ -236,14 +307,20 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
       const float d2 = __ldg(dirs + ((size_t)k * 3 + 2) * NVP + vc);
       const float4 pa = *reinterpret_cast<const float4*>(&s_pm[k][0]);
       const float4 pb = *reinterpret_cast<const float4*>(&s_pm[k][4]);
-      const float pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      const unsigned long long D0 = pk2(d0, d0), D1 = pk2(d1, d1), D2 = pk2(d2, d2);
+      const unsigned long long P[4] = {pk2(pa.x, pa.y), pk2(pa.z, pa.w), pk2(pb.x, pb.y), pk2(pb.z, pb.w)};
 #pragma unroll
-      for (int h = 0; h < HG; ++h) {
-        acc[h][0] = fmaf(d0, pw[h], acc[h][0]);
-        acc[h][1] = fmaf(d1, pw[h], acc[h][1]);
-        acc[h][2] = fmaf(d2, pw[h], acc[h][2]);
+      for (int h = 0; h < HG / 2; ++h) {
+        ffma2(acc2[h][0], D0, P[h]);
+        ffma2(acc2[h][1], D1, P[h]);
+        ffma2(acc2[h][2], D2, P[h]);
       }
     }
+    float acc[HG][3];
+#pragma unroll
+    for (int h = 0; h < HG / 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) unpk2(acc2[h][c], acc[2 * h][c], acc[2 * h + 1][c]);
     float w[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) w[j] = __ldg(m + OFF_W + j * NVP + vc);
@@ -271,27 +348,95 @@ __global__ void __launch_bounds__(VPB) mano_forward_kernel(const ManoParams p) {
       const float z = T[8] * acc[h][0] + T[9] * acc[h][1] + T[10] * acc[h][2] + T[11] - s_ctr[h][2];
       if (!vvalid) continue;
       const int hand = g0 + h;
-      if (p.verts) {
-        float* o = p.verts + ((size_t)hand * NV + v) * 3;
-        o[0] = x; o[1] = y; o[2] = z;
-      }
-      if (p.mc_verts) {          // fused all-gather, one multimem store per value
-        float* o = p.mc_verts + ((size_t)(p.dst_row + hand) * NV + v) * 3;
-        multimem_st_f32(o, x); multimem_st_f32(o + 1, y); multimem_st_f32(o + 2, z);
-      } else if (p.n_peers > 0) {  // fused all-gather, peer stores over NVLink
-        const size_t idx = ((size_t)(p.dst_row + hand) * NV + v) * 3;
-        for (int r = 0; r < p.n_peers; ++r) {
-          float* o = p.peer_verts[r] + idx;
-          o[0] = x; o[1] = y; o[2] = z;
-        }
-      }
-      if (p.verts_camed && p.cam) {
-        float* o = p.verts_camed + ((size_t)hand * NV + v) * 3;
-        o[0] = x * s_pc[h].s + s_pc[h].tx; o[1] = y * s_pc[h].s + s_pc[h].ty; o[2] = z;
+      {   // stage at the offset that matches the global alignment of this hand's chunk (phase 3)
+        const int o = (int)((((size_t)hand * NV + (size_t)blockIdx.y * VPB) * 3) & 3);
+        float* sp = &s_stage[h][o + 3 * t];
+        sp[0] = x; sp[1] = y; sp[2] = z;
       }
       if (tip >= 0) write_joint(p, hand, c_joint_inv[16 + tip], x, y, z, s_pc[h]);
     }
   }
+
+  // ---------------------------------------------------------------- phase 3: 16-byte vertex stores
+  // A hand's chunk is 3*nv contiguous floats at global float index gidx = (hand*778 + v0)*3, which is 8-byte but
+  // not always 16-byte aligned (778*3 = 2 mod 4).  It was staged at offset (gidx & 3) of its shared-memory row, so
+  // 16-byte chunk j of the row IS an aligned 16-byte chunk of global memory: one float4 (or multimem.st.v4 / peer
+  // float4) per thread and chunk; the first / last chunk of a row may be partial and falls back to scalar stores.
+  __syncthreads();
+  {
+    const int v0 = blockIdx.y * VPB;
+    const int nfl = min(VPB, NV - v0) * 3;
+    for (int h = 0; h < HG; ++h) {
+      if (s_side[h] < 0) continue;                      // block-uniform
+      const int hand = g0 + h;
+      const size_t gidx = ((size_t)hand * NV + v0) * 3;
+      const int o = (int)(gidx & 3);
+      const size_t gg = ((size_t)(p.dst_row + hand) * NV + v0) * 3;      // same (gg & 3): dst_row is even
+      const int nchunk = (o + nfl + 3) >> 2;
+      const float sc = s_pc[h].s, tx = s_pc[h].tx, ty = s_pc[h].ty;
+      for (int j = t; j < nchunk; j += VPB) {
+        const float4 q = *reinterpret_cast<const float4*>(&s_stage[h][4 * j]);
+        const float e[4] = {q.x, q.y, q.z, q.w};
+        const int i0 = 4 * j - o;                       // float index inside the chunk of element 0 (may be < 0)
+        const bool full = i0 >= 0 && i0 + 4 <= nfl;
+        float c4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int comp = (i0 + k + 3) % 3;            // i0 + k >= -3
+          c4[k] = comp == 0 ? e[k] * sc + tx : (comp == 1 ? e[k] * sc + ty : e[k]);
+        }
+        if (full) {
+          if (p.verts) *reinterpret_cast<float4*>(p.verts + gidx + i0) = q;
+          if (p.verts_camed && p.cam) *reinterpret_cast<float4*>(p.verts_camed + gidx + i0) = make_float4(c4[0], c4[1], c4[2], c4[3]);
+          if (p.gather) {
+            const unsigned long long off = slot_off + (gg + i0) * 4;
+            if (slot_mc) multimem_st_v4(reinterpret_cast<float*>(p.mc_base + off), q);
+            else for (int r = 0; r < p.world; ++r) *reinterpret_cast<float4*>(p.peer_base[r] + off) = q;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            if (i < 0 || i >= nfl) continue;
+            if (p.verts) p.verts[gidx + i] = e[k];
+            if (p.verts_camed && p.cam) p.verts_camed[gidx + i] = c4[k];
+            if (p.gather) {
+              const unsigned long long off = slot_off + (gg + i) * 4;
+              if (slot_mc) multimem_st_f32(reinterpret_cast<float*>(p.mc_base + off), e[k]);
+              else for (int r = 0; r < p.world; ++r) *reinterpret_cast<float*>(p.peer_base[r] + off) = e[k];
+            }
+          }
+        }
+      }
+    }
+  }
+  }  // if (active)
+
+  // ---------------------------------------------------------------- gather: completion signal
+  // Every CTA (also the ones beyond n) counts itself done after a system-scope fence; the last one to finish
+  // publishes step+1 in the flag word flags[rank] of EVERY rank (release, system scope): whoever acquires that
+  // value sees all vertices and counts of this launch.  No separate barrier kernel, no NCCL call.
+  if (p.gather) {
+    __syncthreads();
+    if (t == 0) {
+      __threadfence_system();
+      const unsigned int total = gridDim.x * gridDim.y;
+      s_last = (atomicAdd(p.done_ctr, 1u) == total - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      if (t == 0) { __threadfence_system(); *p.done_ctr = 0u; }
+      __syncthreads();
+      if (t < p.world)
+        st_release_sys(reinterpret_cast<unsigned long long*>(p.peer_base[t] + p.flags_offset) + p.rank, step + 1);
+      if (t == 0) *p.step_dev = step + 1;
+    }
+  }
+}
+
+// stream-ordered wait until the stores of the most recent gather launch of EVERY rank have landed in this rank's memory
+__global__ void gather_wait_kernel(const unsigned long long* flags, const unsigned long long* step_dev, int world) {
+  if ((int)threadIdx.x < world) wait_flag_ge(flags + threadIdx.x, *step_dev);
 }
 
 // estimate_translation_np (acr/utils.py:430-472) for one hand per thread, fp64 like the numpy original:
@@ -389,15 +534,17 @@ static int mano_forward_impl(const float* model_l, const float* model_r, const f
                              const float* betas, const int32_t* hand_type, int default_side,
                              const int32_t* n_dev, int n_max, int center_idx, const float* cam,
                              const float* offsets, float* verts, float* joints, float* center,
-                             float* verts_camed, float* pj2d, float* pj2d_org, const uint64_t* peer_ptrs, int n_peers,
-                             uint64_t multicast_ptr, int64_t dst_row_offset, void* stream) {
+                             float* verts_camed, float* pj2d, float* pj2d_org, const int32_t* counts_src,
+                             const acr_b200_gather* g, void* stream) {
   ACR_CHECK_ARG(n_max >= 0, "mano_forward: n_max < 0");
-  if (n_max == 0) return ACR_B200_OK;
+  if (n_max == 0 && !g) return ACR_B200_OK;
+  ACR_CHECK_ARG(n_max > 0, "mano_forward_gather: every rank must launch every step (n_max > 0)");
   ACR_CHECK_ARG(poses && betas, "mano_forward: poses/betas are null");
   ACR_CHECK_ARG(default_side == 0 || default_side == 1, "mano_forward: default_side must be 0 or 1");
   ACR_CHECK_ARG(hand_type ? (model_l && model_r) : (default_side ? model_r != nullptr : model_l != nullptr),
                 "mano_forward: missing packed model for a requested side");
   ACR_CHECK_ARG(center_idx >= -1 && center_idx < 21, "mano_forward: center_idx out of range");
+  ACR_CHECK_ARG(((uintptr_t)verts | (uintptr_t)verts_camed) % 16 == 0, "mano_forward: verts / verts_camed must be 16-byte aligned");
   static const int perm[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
   int center_src = -1;
   if (center_idx >= 0) {
@@ -407,18 +554,33 @@ static int mano_forward_impl(const float* model_l, const float* model_r, const f
       return ACR_B200_ENOTSUP;
     }
   }
-  ManoParams p;
+  ManoParams p = {};
   p.model[0] = model_l ? model_l : model_r;
   p.model[1] = model_r ? model_r : model_l;
   p.poses = poses; p.betas = betas; p.hand_type = hand_type; p.default_side = default_side;
   p.n_dev = n_dev; p.n_max = n_max; p.center_src = center_src; p.cam = cam; p.offsets = offsets;
   p.verts = verts; p.joints = joints; p.center = center; p.verts_camed = verts_camed; p.pj2d = pj2d;
   p.pj2d_org = pj2d_org;
-  ACR_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_ptrs || multicast_ptr), "mano_forward_gather: bad peer list");
-  p.n_peers = multicast_ptr ? 0 : n_peers;
-  p.mc_verts = reinterpret_cast<float*>(multicast_ptr);
-  p.dst_row = dst_row_offset;
-  for (int r = 0; r < 8; ++r) p.peer_verts[r] = (peer_ptrs && r < n_peers) ? reinterpret_cast<float*>(peer_ptrs[r]) : nullptr;
+  if (g) {
+    ACR_CHECK_ARG(g->world >= 1 && g->world <= 8 && g->rank >= 0 && g->rank < g->world, "mano_forward_gather: world / rank");
+    ACR_CHECK_ARG(g->rows > 0 && g->rows % 2 == 0 && n_max <= g->rows, "mano_forward_gather: rows per rank must be even and >= n_max");
+    ACR_CHECK_ARG(g->slot_bytes % 16 == 0 && g->counts_offset % 16 == 0 && g->flags_offset % 16 == 0 &&
+                      g->counts_offset >= (uint64_t)g->world * g->rows * NV * 3 * 4 &&
+                      g->slot_bytes >= g->counts_offset + (uint64_t)g->world * 32 && g->flags_offset >= 2 * g->slot_bytes,
+                  "mano_forward_gather: slot layout");
+    ACR_CHECK_ARG(g->local_state && (uintptr_t)g->local_state % 8 == 0, "mano_forward_gather: local_state");
+    p.gather = 1; p.world = g->world; p.rank = g->rank;
+    for (int r = 0; r < g->world; ++r) {
+      ACR_CHECK_ARG(g->peer_base[r] && g->peer_base[r] % 16 == 0, "mano_forward_gather: peer base %d", r);
+      p.peer_base[r] = reinterpret_cast<char*>(g->peer_base[r]);
+    }
+    p.mc_base = reinterpret_cast<char*>(g->multicast_base);
+    p.dst_row = (long long)g->rank * g->rows;
+    p.slot_bytes = g->slot_bytes; p.counts_offset = g->counts_offset; p.flags_offset = g->flags_offset;
+    p.step_dev = reinterpret_cast<unsigned long long*>(g->local_state);
+    p.done_ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(g->local_state) + 8);
+    p.counts_src = counts_src;
+  }
   dim3 grid(ceil_div(n_max, HG), ceil_div(NV, VPB));
   mano_forward_kernel<<<grid, VPB, 0, (cudaStream_t)stream>>>(p);
   ACR_CHECK_LAUNCH();
@@ -431,7 +593,7 @@ extern "C" int acr_b200_mano_forward(const float* model_l, const float* model_r,
                                      const float* offsets, float* verts, float* joints, float* center,
                                      float* verts_camed, float* pj2d, float* pj2d_org, void* stream) {
   return mano_forward_impl(model_l, model_r, poses, betas, hand_type, default_side, n_dev, n_max, center_idx, cam,
-                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, nullptr, 0, 0, 0, stream);
+                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, nullptr, nullptr, stream);
 }
 
 extern "C" int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, const float* poses,
@@ -439,12 +601,19 @@ extern "C" int acr_b200_mano_forward_gather(const float* model_l, const float* m
                                             const int32_t* n_dev, int n_max, int center_idx, const float* cam,
                                             const float* offsets, float* verts, float* joints, float* center,
                                             float* verts_camed, float* pj2d, float* pj2d_org,
-                                            const uint64_t* peer_ptrs, int n_peers, uint64_t multicast_ptr,
-                                            int64_t dst_row_offset, void* stream) {
-  ACR_CHECK_ARG(n_peers > 0, "mano_forward_gather: n_peers must be positive");
+                                            const int32_t* counts_src, const acr_b200_gather* gather, void* stream) {
+  ACR_CHECK_ARG(gather != nullptr, "mano_forward_gather: gather descriptor is null");
   return mano_forward_impl(model_l, model_r, poses, betas, hand_type, default_side, n_dev, n_max, center_idx, cam,
-                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, peer_ptrs, n_peers,
-                           multicast_ptr, dst_row_offset, stream);
+                           offsets, verts, joints, center, verts_camed, pj2d, pj2d_org, counts_src, gather, stream);
+}
+
+extern "C" int acr_b200_gather_wait(const acr_b200_gather* g, void* stream) {
+  ACR_CHECK_ARG(g && g->world >= 1 && g->world <= 8 && g->local_state && g->peer_base[g->rank], "gather_wait: bad descriptor");
+  gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(g->peer_base[g->rank]) + g->flags_offset),
+      reinterpret_cast<const unsigned long long*>(g->local_state), g->world);
+  ACR_CHECK_LAUNCH();
+  return ACR_B200_OK;
 }
 
 extern "C" int acr_b200_cam_trans(const float* j3d, const float* pj2d, const int32_t* n_dev, int n_max,

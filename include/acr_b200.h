@@ -62,21 +62,50 @@ int acr_b200_mano_forward(const float* model_l, const float* model_r, const floa
                           const float* offsets, float* verts, float* joints, float* center,
                           float* verts_camed, float* pj2d, float* pj2d_org, void* stream);
 
-/* Same kernel, with the vertex all-gather FUSED into its epilogue: besides the local `verts`, every
- * vertex is stored straight into the gather buffers of all ranks over NVLink -- either with one
- * `multimem.st` per value through `multicast_ptr` (NVSwitch in-fabric broadcast, NVLS) or, when that is 0,
- * with one peer store per rank through `peer_ptrs[0..n_peers)` (HOST array of device addresses obtained
- * from symmetric memory / CUDA IPC).  Row r of this rank lands at row `dst_row_offset + r` of every
- * gather buffer ((world*R, 778, 3) fp32).  Replaces the gather step of nn.DataParallel
- * (acr/main.py:61) / the separate ncclAllGather of SURVEY.md 8e.  The caller provides the cross-rank
- * barrier after the launch (e.g. the symmetric-memory barrier on the same stream).                    */
+/* Same kernel, with the vertex all-gather FUSED into it (replaces the gather step of nn.DataParallel,
+ * acr/main.py:61 / the separate ncclAllGather of SURVEY.md 8e).  Besides the local outputs, every vertex is
+ * stored straight into the gather buffers of ALL ranks over NVLink: 16-byte `multimem.st.v4.f32` through the
+ * NVLS multicast mapping (the NVSwitch replicates the store) or, when `multicast_base` is 0, one 16-byte peer
+ * store per rank.  The 8 int32 row counts of the shard (`counts_src`, as written by acr_b200_parse) travel the
+ * same way, so the exchange needs no other collective.
+ *
+ * Symmetric allocation (identical layout on every rank, e.g. torch symmetric memory / CUDA IPC / VMM):
+ *     [ slot 0 | slot 1 | flags ]          slot = verts[world][rows][778][3] fp32 at 0,
+ *                                                 counts[world][8] int32 at counts_offset
+ *     flags = uint64[world] at flags_offset (from the allocation base), zero-initialised.
+ * Protocol (all device side, CUDA-graph safe; `local_state` = 16 zero-initialised device-local bytes holding
+ * the step counter and a CTA counter):
+ *   - launch number s (1,2,...) of this entry writes slot s & 1: rank r's rows land at rows [r*rows, (r+1)*rows)
+ *     of that slot on every rank;
+ *   - before touching the slot, the kernel waits until flags[q] >= s-1 for every rank q IN ITS OWN MEMORY: rank q
+ *     publishes s-1 only at the end of its launch s-1, which it enqueued after consuming the data of step s-2
+ *     (CONTRACT: a rank consumes step k's gathered data on the launching stream before its launch k+1) -- so the
+ *     slot is free.  With two slots this dependency is a whole step old: ranks never wait for each other inside a
+ *     step (no barrier), they can drift by up to one step;
+ *   - the last CTA to finish publishes s into flags[rank] of every rank with a system-scope release store after
+ *     a system-scope fence; acr_b200_gather_wait (stream-ordered, tiny) returns once flags[q] >= s for all q in
+ *     this rank's memory, i.e. the data of step s from every rank has landed here.  Rows >= the shard's count
+ *     keep older data: validity is counts[q][2].
+ * `rows` (per rank and slot) must be even and >= n_max; every rank must launch every step.                      */
+typedef struct acr_b200_gather {
+  uint64_t peer_base[8];      /* base address of every rank's allocation, as mapped into THIS process     */
+  uint64_t multicast_base;    /* NVLS multicast mapping of the allocation, or 0                            */
+  int32_t world, rank;
+  int64_t rows;
+  uint64_t slot_bytes;        /* multiple of 16                                                            */
+  uint64_t counts_offset;     /* inside a slot, multiple of 16, >= world*rows*778*3*4                      */
+  uint64_t flags_offset;      /* from the allocation base, multiple of 16, >= 2*slot_bytes                 */
+  void* local_state;          /* device-local, 16 bytes, zero-initialised once                             */
+} acr_b200_gather;
+
 int acr_b200_mano_forward_gather(const float* model_l, const float* model_r, const float* poses,
                                  const float* betas, const int32_t* hand_type, int default_side,
                                  const int32_t* n_dev, int n_max, int center_idx, const float* cam,
                                  const float* offsets, float* verts, float* joints, float* center,
                                  float* verts_camed, float* pj2d, float* pj2d_org,
-                                 const uint64_t* peer_ptrs, int n_peers, uint64_t multicast_ptr,
-                                 int64_t dst_row_offset, void* stream);
+                                 const int32_t* counts_src, const acr_b200_gather* gather, void* stream);
+/* Stream-ordered wait until the most recent gather launch of EVERY rank has landed in this rank's buffer. */
+int acr_b200_gather_wait(const acr_b200_gather* gather, void* stream);
 
 /* Camera translation of every hand from its 21 joints: the closed-form weighted least squares of
  * estimate_translation_np (acr/utils.py:430-472) -- the reference's own fall-back for the host-side

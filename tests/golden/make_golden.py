@@ -23,47 +23,10 @@ REF = "/root/reference"
 
 
 def import_reference():
-    sys.argv = ["make_golden"]
-    # our package dir also contains drop-in `acr` / `mano` packages (regular packages would shadow the
-    # reference's namespace package `mano`), so it is on sys.path only while acr_b200.synth is imported
-    sys.path.insert(0, PKG)
-    import acr_b200.synth  # noqa: F401
-    sys.path.remove(PKG)
-    sys.path.insert(0, REF)
-    os.chdir(REF)
-    for name in ("h5py", "imgaug", "imgaug.augmenters", "chumpy", "chumpy.ch"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
-    sys.modules["imgaug.augmenters"].compute_paddings_to_reach_aspect_ratio = lambda *a, **k: None
-    sys.modules["chumpy"].Ch = object
-    sys.modules["chumpy"].ch = sys.modules["chumpy.ch"]
-    np.float = float
-    np.int = int
-    import torch
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    import acr.config  # noqa: F401  (parses argv + demo.yml at import)
-    import mano.manolayer as ml
-    from acr_b200.synth import make_synthetic_mano
-
-    class _R:  # mimic chumpy's ``.r``
-        def __init__(self, a):
-            self.r = a
-
-    def fake_ready_arguments(path, posekey4vposed="pose"):
-        import scipy.sparse as sp
-        side = "left" if "LEFT" in path else "right"
-        a = make_synthetic_mano(side)
-        d = {k: _R(v) for k, v in a.items() if k in ("betas", "shapedirs", "posedirs", "v_template", "weights")}
-        d["hands_components"] = a["hands_components"]
-        d["hands_mean"] = a["hands_mean"]
-        d["J_regressor"] = sp.csc_matrix(a["J_regressor"])
-        d["f"] = a["f"]
-        d["kintree_table"] = a["kintree_table"]
-        return d
-
-    ml.ready_arguments = fake_ready_arguments
-    return torch
+    """The harness itself lives in oracle/ref_harness.py (shared with the reference arm of bench.py)."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_harness
+    return ref_harness.import_reference(REF, "make_golden")
 
 
 def main():

@@ -1,5 +1,6 @@
-"""2 GPUs (run with `gpurun --gpus 2`): the vertex all-gather fused into the MANO kernel (symmetric-memory
-peer / multimem stores over NVLink) must equal an NCCL all-gather of the same vertices."""
+"""2 GPUs (run with `gpurun --gpus 2`; log kept in profiles/): the vertex all-gather fused into the MANO kernel
+(symmetric-memory 16-byte peer / multimem stores over NVLink, double-buffered slots, arrival flags, counts carried
+along -- no barrier, no NCCL call) must equal an NCCL all-gather of the same vertices, step after step."""
 import os
 import socket
 
@@ -30,29 +31,56 @@ def _worker(rank, world, port, q, use_mc):
         ml = ops.pack_mano_model(make_synthetic_mano("left"), True, dev)
         mr = ops.pack_mano_model(make_synthetic_mano("right"), False, dev)
         R = 64
-        g = torch.Generator().manual_seed(10 + rank)
-        poses = (torch.randn(R, 48, generator=g) * 0.5).to(dev)
-        betas = torch.randn(R, 10, generator=g).to(dev)
-        ht = (torch.arange(R) % 2).int().to(dev)
-        n_valid = 40 + 7 * rank
-        n_dev = torch.tensor([n_valid], dtype=torch.int32, device=dev)
         pg = PeerVertexGather(R, dev, use_multicast=use_mc)
-        pg.buf.fill_(-7.0)
+        nfl = world * R * 778 * 3 * 4
+        for s in range(2):                                   # sentinel in the vertex area of both slots (flags stay 0)
+            pg.buf[s * pg.slot_bytes: s * pg.slot_bytes + nfl].view(torch.float32).fill_(-7.0)
         torch.cuda.synchronize()
         dist.barrier()
-        out = ops.mano_forward(ml, mr, poses, betas, ht, 1, 9, n_dev=n_dev, peers=pg)
+        ht = (torch.arange(R) % 2).int().to(dev)
+        ok, why = True, ""
+
+        def launch(step):
+            g = torch.Generator().manual_seed(1000 * step + rank)
+            poses = (torch.randn(R, 48, generator=g) * 0.5).to(dev)
+            betas = torch.randn(R, 10, generator=g).to(dev)
+            n_valid = 40 + 7 * rank - 3 * step                # shrinking: rows beyond keep OLDER data, counts say so
+            counts = torch.zeros(8, dtype=torch.int32, device=dev)
+            counts[2], counts[0], counts[1] = n_valid, n_valid // 2, n_valid - n_valid // 2
+            if (step + rank) % 2 == 0:
+                torch.cuda._sleep(int(3e7))                   # skew the ranks (~15 ms) to exercise the drift
+            out = ops.mano_forward(ml, mr, poses, betas, ht, 1, 9, n_dev=counts[2:3], peers=pg, counts=counts)
+            return out, counts
+
+        # (a) every step consumed: finish(), compare every shard with an NCCL all-gather of the same step
+        for step in range(1, 7):
+            out, counts = launch(step)
+            pg.finish()
+            ref, cnt = gather_vertices(out["verts"], counts)
+            torch.cuda.synchronize()
+            got, gcnt = pg.gathered(), pg.counts()
+            if not torch.equal(gcnt, cnt):
+                ok, why = False, f"step {step}: counts {gcnt.tolist()} != {cnt.tolist()}"
+            for r in range(world):
+                nv = int(cnt[r, 2])
+                if not torch.equal(got[r, :nv], ref[r, :nv]):
+                    ok, why = False, f"step {step}: shard {r} differs"
+            if step == 1:
+                for r in range(world):
+                    if not bool((got[r, int(cnt[r, 2]):] == -7.0).all()):
+                        ok, why = False, "rows >= n_dev were written"
+        # (b) four launches back to back without any wait in between (ranks drift), then one finish()
+        last = None
+        for step in range(7, 11):
+            last = launch(step)
         pg.finish()
+        ref, cnt = gather_vertices(last[0]["verts"], last[1])
         torch.cuda.synchronize()
-        counts = torch.zeros(8, dtype=torch.int32, device=dev)
-        counts[2] = n_valid
-        ref, cnt = gather_vertices(out["verts"], counts)
-        torch.cuda.synchronize()
-        ok = True
         for r in range(world):
             nv = int(cnt[r, 2])
-            ok = ok and torch.equal(pg.gathered()[r, :nv], ref[r, :nv])
-            ok = ok and bool((pg.gathered()[r, nv:] == -7.0).all())      # rows >= n_dev are never written
-        q.put((rank, bool(ok), pg.mode))
+            if not (torch.equal(pg.gathered()[r, :nv], ref[r, :nv]) and torch.equal(pg.counts(), cnt)):
+                ok, why = False, f"back-to-back: shard {r} differs"
+        q.put((rank, bool(ok), why or pg.mode))
         dist.barrier()
     except Exception as e:  # noqa: BLE001
         q.put((rank, False, repr(e)))
@@ -62,6 +90,8 @@ def _worker(rank, world, port, q, use_mc):
 
 @pytest.mark.parametrize("use_mc", [False, True])
 def test_fused_vertex_all_gather_2gpu(use_mc):
+    """Ten steps on 2 GPUs with skewed ranks: double-buffered slots, flags instead of barriers, counts carried in
+    the symmetric buffer; every shard of every consumed step must equal the NCCL all-gather bit for bit."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp

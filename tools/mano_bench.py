@@ -15,7 +15,7 @@ from acr_b200.synth import make_synthetic_mano  # noqa: E402
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
 ml = ops.pack_mano_model(make_synthetic_mano("left"), True, "cuda")
 mr = ops.pack_mano_model(make_synthetic_mano("right"), False, "cuda")
-for n in (2, 512, 8192, 65536):
+for n in tuple(int(v) for v in os.environ.get('MANO_BENCH_N', '512,65536').split(',')):
     g = torch.Generator().manual_seed(0)
     poses = (torch.randn(n, 48, generator=g) * 0.5).cuda()
     betas = torch.randn(n, 10, generator=g).cuda()
