@@ -21,9 +21,12 @@
 //     is pulled through L2 3.4x instead of 9x.
 //   * persistent CTAs (one per SM) loop over tiles; weights stay resident in shared memory when they
 //     fit (all 32/64-channel layers), otherwise they stream through their own mbarrier ring.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread issues tcgen05.mma, fp32 accumulators
-//     in TMEM, double buffered), warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) (ReLU) ->
-//     16-bit / fp32 NHWC) overlapping the next tile's main loop.
+//   * warp 0 = TMA producer; warps 1..2 = MMA issuers, ONE PER HALF of the 16x16 super-tile (each an elected
+//     thread issuing tcgen05.mma into its own fp32 accumulator in TMEM, double buffered): the issue rate of a
+//     single thread (a dependent stream of uniform-datapath instructions, ~72 clk per 128x64x16 MMA against 32
+//     clk of math) was the bound of the N = 64 layers, two independent issuers double it; 8 epilogue warps
+//     (tcgen05.ld -> +bias (+residual) (ReLU) -> 16-bit / fp32 NHWC) overlap the next tile's main loop.
+//     -DACR_DUAL_ISSUER=0 builds the single-issuer form (A/B measurements).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -169,8 +172,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // size (4 KB .. 72 KB), a 2-D box ~320 clk.  So the CTA works on 16x16-pixel super-tiles: ONE box per
 // (channel chunk, kx) feeds two M=128 UMMA tiles (left / right 8 columns) and three ky taps.
 constexpr int TILE_Y = 16, TILE_X = 16, HALF_X = 8, TILE_M = 128;
+#ifndef ACR_DUAL_ISSUER
+#define ACR_DUAL_ISSUER 1
+#endif
+constexpr bool DUAL = ACR_DUAL_ISSUER != 0;
+constexpr int ISSUERS = DUAL ? 2 : 1;        // MMA-issuing warps (one per half-tile accumulator when 2)
+constexpr int EPI_WARP0 = 1 + ISSUERS;       // first epilogue warp
 constexpr int EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TC_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int SMEM_BUDGET = 224 * 1024;
 
 struct ConvTcParams {
@@ -189,6 +198,7 @@ struct ConvTcParams {
   int vec256;   // output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int ksteps;   // k16 steps of a chunk that hold real channels (the rest are TMA zero fill: skipped)
   int patch_mode, b_resident, SA, SB;
+  int patch1;   // MODE_P1: ONE 24-wide haloed box per channel chunk, kx shifts through the descriptor base offset
   uint32_t a_stage_bytes, b_block_bytes, b_region_bytes;
   int tmem_cols, acc_stride, nbuf;
   int tiles_x, tiles_per_img, total_tiles, Ho, Wo, out_stride, res_stride;
@@ -209,6 +219,14 @@ struct SwizzleCfg {
 
 // MODE bits (compile-time specialisation of the single-thread MMA issue loop)
 constexpr int MODE_PATCH = 1, MODE_RESIDENT = 2, MODE_XPAIR = 4;
+// MODE_P1 (with MODE_PATCH, CK = 64): the whole haloed input patch of a super-tile is ONE TMA box {64, 24, 18} per channel
+// chunk (x0-1 .. x0+22, y0-1 .. y0+16; the row pitch of 24 pixels keeps every image row on a swizzle-atom boundary).
+// The nine taps are nine UMMA descriptors into it: ky moves the start by whole image rows, kx by single pixels --
+// a start address that is NOT aligned to the 1024-byte swizzle repeat, which the descriptor's base-offset field
+// ((start >> 7) & 7 = kx) declares.  One box instead of three: a third of the TMA issues, half the L2 -> smem
+// bytes, half the shared memory per tile (so a whole tile of look-ahead fits next to resident weights).
+constexpr int MODE_P1 = 16;
+constexpr int P1_PITCH = 24;   // pixels per image row of the single box
 // MODE_DIAG: diagnostic instances (tools/conv_bench.py, ACR_B200_CONV_DIAG=bits): 1 = the issuer skips the MMAs,
 // 2 = the epilogue only recycles the accumulator, 4 = the epilogue reads TMEM but skips math and stores.  Timing
 // floors of each warp role; never launched by the product path (debug == 0).
@@ -218,6 +236,8 @@ template <int CK, typename T, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using Cfg = SwizzleCfg<CK>;
   constexpr bool PATCH = (MODE & MODE_PATCH) != 0, RESIDENT = (MODE & MODE_RESIDENT) != 0, XPAIR = (MODE & MODE_XPAIR) != 0;
+  constexpr bool P1 = (MODE & MODE_P1) != 0;
+  static_assert(!P1 || (PATCH && CK == 64), "the single-box form exists for CK = 64 patch convs");
   constexpr bool DIAG = (MODE & MODE_DIAG) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -228,28 +248,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t stage_base = a_base + (uint32_t)SA * P.a_stage_bytes;  // epilogue staging: 2 halves x [128 px][128 B]
   const uint32_t bias_base = stage_base + P.stage_out_bytes;            // fp32 bias[npad] (<= 1 KB)
   const uint32_t bar_base = bias_base + 1024u;
-  // barrier map: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] bres tmem_full[2] tmem_empty[2] | tmem_ptr
+  // barrier map: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] bres tmem_full[buf][half] tmem_empty[buf][half] | tmem_ptr
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
   auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
   auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
   const uint32_t bres_bar = bar_base + 8u * (2 * SA + 2 * SB);
-  auto tmem_full = [&](int b) { return bres_bar + 8u * (1 + b); };
-  auto tmem_empty = [&](int b) { return bres_bar + 8u * (3 + b); };
-  const uint32_t tmem_ptr_addr = bres_bar + 8u * 5;
+  auto tmem_full = [&](int b, int h) { return bres_bar + 8u * (1 + b * 2 + h); };
+  auto tmem_empty = [&](int b, int h) { return bres_bar + 8u * (5 + b * 2 + h); };
+  const uint32_t tmem_ptr_addr = bres_bar + 8u * 9;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nA = P.patch_mode ? P.cchunks * 3 : P.taps * P.cchunks;  // A loads per super-tile
-  const int nsub = P.patch_mode ? 3 : 1;                             // taps served by one A load
+  const int nA = P.patch1 ? P.cchunks : (P.patch_mode ? P.cchunks * 3 : P.taps * P.cchunks);  // A loads per super-tile
+  const int nsub = P.patch1 ? 9 : (P.patch_mode ? 3 : 1);                                     // taps served by one A load
   const int nbuf = P.nbuf;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    // a stage is free again once EVERY issuer's MMAs have read it (tcgen05.commit tracks the issuing thread's MMAs only)
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), ISSUERS); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), ISSUERS); }
     mbar_init(bres_bar, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), EPI_WARPS); }
+    for (int b = 0; b < 2; ++b)
+      for (int h = 0; h < 2; ++h) { mbar_init(tmem_full(b, h), 1); mbar_init(tmem_empty(b, h), EPI_WARPS / 2); }
     fence_barrier_init();
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
@@ -285,7 +307,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int y0 = (rem / P.tiles_x) * TILE_Y, x0 = (rem % P.tiles_x) * TILE_X;
         for (int a = 0; a < nA; ++a) {
           int cc, view = 0, dy = 0, dx = 0, tap0;
-          if (P.patch_mode) {           // one 18x16 box per (channel chunk, kx); rows y0-1 .. y0+16
+          if (P.patch1) {               // one 18x24 box per channel chunk: rows y0-1 .. y0+16, columns x0-1 .. x0+22
+            cc = a; dy = -1; dx = -1; tap0 = 0;
+          } else if (P.patch_mode) {    // one 18x16 box per (channel chunk, kx); rows y0-1 .. y0+16
             cc = a / 3; const int kx = patch_kx(a % 3, P.xpair);
             dy = -1; dx = kx - 1; tap0 = kx;
           } else {
@@ -309,7 +333,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (++sa == SA) { sa = 0; pha ^= 1u; }
           if (!P.b_resident) {
             for (int sub = 0; sub < nsub; ++sub) {
-              const int tap = P.patch_mode ? sub * 3 + tap0 : tap0;
+              // weight block order = the issuer's tap order (single box: ky-major, kx 1,0,2 for x-paired convs)
+              const int tap = P.patch1 ? (sub / 3) * 3 + patch_kx(sub % 3, P.xpair) : (P.patch_mode ? sub * 3 + tap0 : tap0);
               mbar_wait(emptyB(sb), phb ^ 1u);
               if (elect_one_sync()) {
                 mbar_expect_tx(fullB(sb), P.b_block_bytes);
@@ -322,29 +347,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================================================================= MMA issuer
-    // ONE elected thread runs the whole issue loop.  It is a single dependent instruction stream, so every
-    // integer / branch instruction in it sits on the tensor pipe's critical path (ncu source view of the
-    // previous version: the issuing warp never waited for data, it spent ~110 clk per MMA pair on its own
-    // bookkeeping).  Hence: mode flags are template constants, the tap / k-step loops are fully unrolled,
-    // descriptors advance by adding constants to one 32-bit word.
+  } else if (warp < EPI_WARP0) {
+    // ====================================================================== MMA issuer(s)
+    // ONE elected thread per issuing warp runs the whole issue loop.  It is a single dependent instruction stream, so
+    // every integer / branch instruction in it sits on the tensor pipe's critical path (ncu source view: the issuing
+    // warp never waited for data, it spent its time on its own bookkeeping).  Hence: mode flags are template
+    // constants, the tap / k-step loops are fully unrolled, descriptors advance by adding constants to one 32-bit
+    // word -- and with DUAL the two halves of the super-tile have an issuer each (warp 1: left 8 columns, warp 2:
+    // right 8 columns), each with its own accumulator and its own full/empty barriers towards the epilogue.
     if (RESIDENT) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     if (elect_one_sync()) {
+      constexpr int NH = DUAL ? 1 : 2;                 // halves issued by this thread
+      const int h0 = DUAL ? warp - 1 : 0;              // first half issued by this thread
       // descriptor words that never change (see make_smem_desc): hi = SBO | version | layout, lo = addr>>4 | LBO
       const uint32_t hi_a = (Cfg::kSBO_A >> 4) | (1u << 14) | (Cfg::kLayout << 29);
       const uint32_t hi_b = (Cfg::kAtom >> 4) | (1u << 14) | (Cfg::kLayout << 29);
       const uint32_t lo_flags = 1u << 16;
       const uint32_t idesc = P.idesc, idesc_half = P.idesc_half, acc_stride = (uint32_t)P.acc_stride;
       const uint32_t b_block16 = P.b_block_bytes >> 4, a_stage16 = P.a_stage_bytes >> 4;
-      const uint32_t a_lo_base = ((a_base >> 4) & 0x3FFF) | lo_flags, b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
+      // the right half's rows start one swizzle atom (8 pixels) into every image row of the box
+      const uint32_t a_lo_base = (((a_base >> 4) & 0x3FFF) | lo_flags) + (uint32_t)h0 * (Cfg::kAtom >> 4);
+      const uint32_t b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
       const int cchunks = P.cchunks, ksteps = P.ksteps, taps = P.taps;
       const bool full_k = ksteps == CK / 16;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
-      // the MMAs of one (A stage, tap): both halves of the super-tile, every k16 step of the chunk
-      auto issue = [&](uint32_t d0, uint32_t d1, uint32_t a_tap, uint32_t b_lo, uint32_t first, int kx) {
+      // the MMAs of one (A stage, tap): this thread's half / halves of the super-tile, every k16 step of the chunk
+      auto issue_hi = [&](uint32_t d0, uint32_t a_tap, uint32_t hi_a, uint32_t b_lo, uint32_t first, int kx) {
         if (DIAG && (P.debug & 1)) return;
         if (XPAIR && kx != 1) {
           // side taps of the x-paired conv connect ONE pixel of the neighbouring pair to ONE of ours: a 32x32
@@ -354,34 +384,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int ks = ks0; ks < ks0 + 2; ++ks) {
             const uint32_t f = (ks == ks0) ? first : 1u;
-            umma_f16_lohi(d0 + dcol, a_tap + ks * 2, hi_a, b_lo + brow + ks * 2, hi_b, idesc_half, f);
-            umma_f16_lohi(d1 + dcol, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + brow + ks * 2, hi_b, idesc_half, f);
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh)
+              umma_f16_lohi(d0 + hh * acc_stride + dcol, a_tap + hh * (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + brow + ks * 2, hi_b, idesc_half, f);
           }
         } else if (full_k) {   // one straight-line block: nothing between the MMAs but descriptor adds
 #pragma unroll
           for (int ks = 0; ks < CK / 16; ++ks) {
             const uint32_t f = (ks == 0) ? first : 1u;
-            umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);                        // left 8 columns
-            umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);  // right 8 columns
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh)
+              umma_f16_lohi(d0 + hh * acc_stride, a_tap + hh * (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
           }
         } else {               // 33/34-channel inputs: the zero-filled tail of the chunk is skipped
 #pragma unroll
           for (int ks = 0; ks < CK / 16; ++ks) {
             if (ks < ksteps) {
               const uint32_t f = (ks == 0) ? first : 1u;
-              umma_f16_lohi(d0, a_tap + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
-              umma_f16_lohi(d1, a_tap + (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh)
+                umma_f16_lohi(d0 + hh * acc_stride, a_tap + hh * (Cfg::kAtom >> 4) + ks * 2, hi_a, b_lo + ks * 2, hi_b, idesc, f);
             }
           }
         }
       };
+      auto issue = [&](uint32_t d0, uint32_t a_tap, uint32_t b_lo, uint32_t first, int kx) { issue_hi(d0, a_tap, hi_a, b_lo, first, kx); };
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;   // how often this buffer was used before
-        mbar_wait(tmem_empty(buf), (use & 1u) ^ 1u);  // epilogue drained this accumulator pair
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) mbar_wait(tmem_empty(buf, h0 + hh), (use & 1u) ^ 1u);  // epilogue drained the accumulator(s)
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)buf * 2u * acc_stride, d1 = d0 + acc_stride;
-        if (PATCH) {
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 + h0) * acc_stride;
+        if (P1) {
+          // one A stage per channel chunk; tap (ky,kx) starts (ky * 24 + kx) pixels into it (+ 8 for the right half)
+          constexpr uint32_t SBO1 = P1_PITCH * Cfg::kRowBytes;
+          for (int cc = 0; cc < cchunks; ++cc) {
+            mbar_wait(fullA(sa), pha);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo_base + (uint32_t)sa * a_stage16;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const int kx = XPAIR ? (i == 0 ? 1 : (i == 1 ? 0 : 2)) : i;
+                uint32_t b_lo;
+                if (RESIDENT) b_lo = b_lo_base + (uint32_t)((ky * 3 + kx) * cchunks + cc) * b_block16;
+                else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
+                const uint32_t first = (ky == 0 && i == 0) ? (cc != 0 ? 1u : 0u) : 1u;
+                // base offset = swizzle phase of the first row = kx (rows are 128 B, every image row starts a repeat)
+                const uint32_t hi1 = (SBO1 >> 4) | (1u << 14) | ((P.debug & 16) ? 0u : ((uint32_t)kx << 17)) | (Cfg::kLayout << 29);
+                issue_hi(d0, a_lo + (uint32_t)(ky * P1_PITCH + kx) * (Cfg::kRowBytes >> 4), hi1, b_lo, first, kx);
+                if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
+              }
+            }
+            umma_commit(emptyA(sa));
+            if (++sa == SA) { sa = 0; pha ^= 1u; }
+          }
+        } else if (PATCH) {
           // one A stage per (channel chunk, kx): rows y0-1 .. y0+16, the three ky taps are 16-pixel row shifts
           for (int cc = 0; cc < cchunks; ++cc) {
 #pragma unroll
@@ -396,10 +456,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (RESIDENT) b_lo = b_lo_base + (uint32_t)((sub * 3 + kx) * cchunks + cc) * b_block16;
                 else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
                 const uint32_t first = (i == 0 && sub == 0) ? (cc != 0 ? 1u : 0u) : 1u;
-                issue(d0, d1, a_lo + (uint32_t)sub * (Cfg::kSBO_A >> 4), b_lo, first, kx);
+                issue(d0, a_lo + (uint32_t)sub * (Cfg::kSBO_A >> 4), b_lo, first, kx);
                 if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
               }
-              umma_commit(emptyA(sa));  // frees the A stage once these MMAs have read it
+              umma_commit(emptyA(sa));  // this issuer's MMAs have read the A stage
               if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
           }
@@ -413,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               uint32_t b_lo;
               if (RESIDENT) { b_lo = b_res; b_res += b_block16; }
               else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
-              issue(d0, d1, a_lo_base + (uint32_t)sa * a_stage16, b_lo, first, 1);
+              issue(d0, a_lo_base + (uint32_t)sa * a_stage16, b_lo, first, 1);
               first = 1u;
               if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
               umma_commit(emptyA(sa));
@@ -421,14 +481,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         }
-        umma_commit(tmem_full(buf));  // both accumulators of this super-tile complete
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) umma_commit(tmem_full(buf, h0 + hh));  // this thread's accumulator(s) complete
       }
     }
     __syncwarp();
   } else {
     // ========================================================================= epilogue
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
-    const int h = (warp - 2) >> 2;         // which half (accumulator) of the super-tile
+    const int h = (warp - EPI_WARP0) >> 2; // which half (accumulator) of the super-tile
     const int r = q * 32 + lane;
     // TMA-store path: a warp's direct stores put every lane on its own 128-byte line (32 LSU wavefronts per
     // instruction -- ncu: l1tex data pipe 77 % busy, the epilogue was the bound of the N = 64 layers); staging
@@ -460,12 +521,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
       }
-      mbar_wait(tmem_full(buf), use & 1u);
+      mbar_wait(tmem_full(buf, h), use & 1u);
       tc_fence_after();
       if (DIAG && (P.debug & 2)) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(buf));
+        if (lane == 0) mbar_arrive(tmem_empty(buf, h));
         continue;
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
@@ -479,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (g0 + 64 >= P.npad) {  // all TMEM reads of this tile done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty(buf));
+          if (lane == 0) mbar_arrive(tmem_empty(buf, h));
         }
         if (DIAG && (P.debug & 4)) continue;
         if (tma_out) {            // the previous slab's TMA store must have finished READING the staging buffer
@@ -546,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   }
-  if (warp >= 2 && P.tma_out && ((warp & 3) * 32 + (threadIdx.x & 31)) == 0) bulk_wait_all();  // staging must outlive the stores
+  if (warp >= EPI_WARP0 && P.tma_out && ((warp & 3) * 32 + (threadIdx.x & 31)) == 0) bulk_wait_all();  // staging must outlive the stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -608,6 +669,13 @@ static bool tma_out_disabled() {
   return !(e && atoi(e) != 0);
 }
 
+// The single-box A operand (MODE_P1) is on by default; ACR_B200_P1=0 (read at plan creation) selects the three
+// kx-shifted boxes again (A/B timing).  ACR_B200_CONV_DIAG bit 16 zeroes the descriptor base offset (hardware probe).
+static bool p1_enabled() {
+  const char* e = getenv("ACR_B200_P1");
+  return !(e && atoi(e) == 0);
+}
+
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x16 super-tile", a.out.H, a.out.W);
   ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 256,
@@ -621,7 +689,9 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ConvTcParams& p = pl->p;
   pl->ck = ck; pl->act_dtype = act_dtype;
   p.patch_mode = (a.k == 3 && a.stride == 1) ? 1 : 0;
+  p.patch1 = (p.patch_mode && ck == 64 && p1_enabled()) ? 1 : 0;
   const cuuint32_t box_rows = p.patch_mode ? TILE_Y + 2 : TILE_Y;
+  const cuuint32_t box_cols = p.patch1 ? P1_PITCH : TILE_X;
   const cuuint64_t esz = 2;
   const cuuint64_t dim0 = (cuuint64_t)(a.cin_pad < a.in.pix_stride ? a.cin_pad : a.in.pix_stride);
   int rc = ACR_B200_OK;
@@ -629,7 +699,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     cuuint64_t dims[4] = {dim0, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.batch};
     cuuint64_t str[3] = {(cuuint64_t)a.in.pix_stride * esz, (cuuint64_t)a.in.W * a.in.pix_stride * esz,
                          (cuuint64_t)a.in.H * a.in.W * a.in.pix_stride * esz};
-    cuuint32_t box[4] = {(cuuint32_t)ck, TILE_X, box_rows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)ck, box_cols, box_rows, 1};
     rc = encode(&p.tmA[0], act_dtype, 4, a.in.ptr, dims, str, box, ck);
     for (int v = 1; v < 4 && !rc; ++v) p.tmA[v] = p.tmA[0];
   } else {
@@ -685,25 +755,27 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.cout_pad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.idesc_half = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   // shared-memory plan
-  p.a_stage_bytes = (uint32_t)(box_rows * TILE_X) * ck * 2;
+  p.a_stage_bytes = (uint32_t)(box_rows * box_cols) * ck * 2;
   p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
   const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
   p.tma_out = want_tma_out ? 1 : 0;
   p.stage_out_bytes = p.tma_out ? 2u * 16384u : 0u;
   const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
-  const int nA = p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks;
-  p.b_resident = (b_total + 3 * (size_t)p.a_stage_bytes + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
+  const int nA = p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks);
+  const size_t min_a = (p.patch1 ? 2 : 3) * (size_t)p.a_stage_bytes;   // a single-box stage already is a whole tile (per chunk)
+  p.b_resident = (b_total + min_a + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
   if (p.b_resident) {
     p.b_region_bytes = (uint32_t)((b_total + 1023) & ~(size_t)1023);
     p.SB = 0;
   } else {
     p.SB = 4;
-    while (p.SB > 2 && (size_t)p.SB * p.b_block_bytes + 3 * (size_t)p.a_stage_bytes + fixed > (size_t)SMEM_BUDGET) --p.SB;
+    while (p.SB > 2 && (size_t)p.SB * p.b_block_bytes + min_a + fixed > (size_t)SMEM_BUDGET) --p.SB;
     p.b_region_bytes = (uint32_t)(((size_t)p.SB * p.b_block_bytes + 1023) & ~(size_t)1023);
   }
   int SA = (int)(((size_t)SMEM_BUDGET - fixed - p.b_region_bytes) / p.a_stage_bytes);
   if (SA > 8) SA = 8;
-  if (SA > 2 * nA) SA = 2 * nA;  // no point in more stages than two super-tiles' worth of loads
+  if (SA > 2 * nA && !p.patch1) SA = 2 * nA;  // no point in more stages than two super-tiles' worth of loads
+  if (p.patch1 && SA > 4) SA = 4;
   if (SA < 2) { set_error("conv_tc: shared memory plan does not fit (cout_pad %d, ck %d)", a.cout_pad, ck); delete pl; return ACR_B200_EINVAL; }
   p.SA = SA;
   pl->smem = fixed + p.b_region_bytes + (size_t)SA * p.a_stage_bytes;
@@ -735,6 +807,15 @@ static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
 template <int CK, typename T>
 static int launch_mode(const ConvTcPlan* pl, cudaStream_t st) {
   const int mode = (pl->p.patch_mode ? MODE_PATCH : 0) | (pl->p.b_resident ? MODE_RESIDENT : 0);
+  if (CK == 64 && pl->p.patch1) {
+    if (pl->p.debug & ~16) { set_error("conv_tc: diagnostic instances exist for the three-box form only (ACR_B200_P1=0)"); return ACR_B200_EINVAL; }
+    if (pl->p.xpair) {
+      if (!pl->p.b_resident) { set_error("conv_tc: x-paired conv needs resident weights"); return ACR_B200_EINVAL; }
+      return launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR | MODE_P1>(pl, st);
+    }
+    return pl->p.b_resident ? launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_P1>(pl, st)
+                            : launch_inst<64, T, MODE_PATCH | MODE_P1>(pl, st);
+  }
   if (pl->p.debug) {
     if (CK != 64 || mode != (MODE_PATCH | MODE_RESIDENT)) { set_error("conv_tc: diagnostic instances exist for CK=64 patch/resident only"); return ACR_B200_EINVAL; }
     return pl->p.xpair ? launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR | MODE_DIAG>(pl, st)
