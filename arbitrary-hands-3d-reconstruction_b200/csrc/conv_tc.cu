@@ -100,6 +100,11 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -185,7 +190,9 @@ constexpr int SMEM_BUDGET = 224 * 1024;
 struct ConvTcParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
-  CUtensorMap tmOut;   // output as {C, W, H, B}, box {64, 8, 16, 1}, 128B swizzle (tma_out)
+  CUtensorMap tmOut;   // output as {C, W, H, B}, box {64, 8, 16, 1} (tma_out) or {64, 8, 4, 1} (epi_staged), 128B swizzle
+  CUtensorMap tmRes;   // residual, box {64, 8, 4, 1}, 128B swizzle (epi_staged)
+  int epi_staged;      // N = 64, 16-bit output: every epilogue warp stages its 32 px x 128 B in shared memory, TMA in/out
   const float* bias;
   const void* res;
   void* out;
@@ -257,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto tmem_full = [&](int b, int h) { return bres_bar + 8u * (1 + b * 2 + h); };
   auto tmem_empty = [&](int b, int h) { return bres_bar + 8u * (5 + b * 2 + h); };
   const uint32_t tmem_ptr_addr = bres_bar + 8u * 9;
+  auto res_full = [&](int w) { return bres_bar + 8u * (10 + w); };   // staged epilogue: residual box of warp w has landed
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
@@ -272,10 +280,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     mbar_init(bres_bar, 1);
     for (int b = 0; b < 2; ++b)
       for (int h = 0; h < 2; ++h) { mbar_init(tmem_full(b, h), 1); mbar_init(tmem_empty(b, h), EPI_WARPS / 2); }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(res_full(w), 1);
     fence_barrier_init();
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
-    if (P.tma_out) tma_prefetch_desc(&P.tmOut);
+    if (P.tma_out || P.epi_staged) tma_prefetch_desc(&P.tmOut);
+    if (P.epi_staged && P.has_res) tma_prefetch_desc(&P.tmRes);
   }
   if (!P.bias_per_image)
     for (int i = threadIdx.x; i < P.npad; i += TC_THREADS) s_bias[i] = P.bias[i];
@@ -499,6 +509,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t stage_sw = (uint32_t)(r & 7);
     int it = 0;
     pdl_wait();   // residual / per-image bias reads and every output write wait for the previous kernel
+    if (P.epi_staged && !DIAG) {
+      // ----------------------------------------------------------------- staged epilogue (N = 64, 16-bit output)
+      // Direct global accesses put every lane of a warp on its own 128-byte line (32 LSU wavefronts per instruction,
+      // ncu: l1tex data pipe 77 % busy) and keep the residual's DRAM latency inside the per-tile critical path.
+      // Here every epilogue warp owns a 4 KB buffer = its 32 pixels (4 rows x 8 columns of the half tile) x 128 B in
+      // the 128B-swizzled layout of a TMA box {64, 8, 4}: the residual of the NEXT tile is fetched into it by a TMA
+      // load (asynchronous, one mbarrier per warp) as soon as the previous output has left, a thread reads / writes
+      // only its own row (conflict-free 16-byte accesses), and the result leaves with one TMA store per warp.
+      // Synchronisation is per warp only: __syncwarp + proxy fences, no CTA-wide barrier.
+      const int wi = warp - EPI_WARP0;
+      const uint32_t my_stage = stage_base + (uint32_t)wi * 4096u;
+      const uint32_t row = my_stage + (uint32_t)lane * 128u;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      const bool has_res = P.has_res != 0;
+      uint32_t res_phase = 0;
+      auto tile_xy = [&](int tile, int& n, int& tx, int& ty) {
+        n = tile / P.tiles_per_img;
+        const int rem = tile % P.tiles_per_img;
+        ty = (rem / P.tiles_x) * TILE_Y + 4 * q;
+        tx = (rem % P.tiles_x) * TILE_X + h * HALF_X;
+      };
+      if (has_res && (int)blockIdx.x < P.total_tiles && lane == 0) {
+        int n, tx, ty;
+        tile_xy(blockIdx.x, n, tx, ty);
+        mbar_expect_tx(res_full(wi), 4096u);
+        tma_load_4d(my_stage, &P.tmRes, res_full(wi), 0, tx, ty, n);
+      }
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
+        int n, tx, ty;
+        tile_xy(tile, n, tx, ty);
+        mbar_wait(tmem_full(buf, h), use & 1u);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(t_row + (uint32_t)(c * 16), v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(buf, h));      // accumulator back to the issuer
+        if (has_res) {
+          mbar_wait(res_full(wi), res_phase);                  // this tile's residual box has landed
+          res_phase ^= 1u;
+        } else {
+          if (lane == 0) bulk_wait_read0();                    // the previous store has finished reading the buffer
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 16 + 4 * i);
+            f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
+          }
+          const uint32_t a0 = row + ((((uint32_t)(2 * c)) ^ sw) << 4), a1 = row + ((((uint32_t)(2 * c + 1)) ^ sw) << 4);
+          if (has_res) {
+            float x[16];
+            unpack8<T>(lds128(a0), x);
+            unpack8<T>(lds128(a1), x + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += x[i];
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          sts128(a0, pack8<T>(f));
+          sts128(a1, pack8<T>(f + 8));
+        }
+        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&P.tmOut, my_stage, 0, tx, ty, n);
+          bulk_commit();
+          const int next = tile + (int)gridDim.x;
+          if (has_res && next < P.total_tiles) {               // refill the buffer with the next tile's residual
+            bulk_wait_read0();
+            int n2, tx2, ty2;
+            tile_xy(next, n2, tx2, ty2);
+            mbar_expect_tx(res_full(wi), 4096u);
+            tma_load_4d(my_stage, &P.tmRes, res_full(wi), 0, tx2, ty2, n2);
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) bulk_wait_all();                          // staging must outlive the stores
+    } else
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
       const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
@@ -676,6 +777,12 @@ static bool p1_enabled() {
   return !(e && atoi(e) == 0);
 }
 
+// ACR_B200_EPI=0 (read at plan creation) selects the direct-store epilogue for the N = 64 layers (A/B timing).
+static bool epi_staged_enabled() {
+  const char* e = getenv("ACR_B200_EPI");
+  return !(e && atoi(e) == 0);
+}
+
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x16 super-tile", a.out.H, a.out.W);
   ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 256,
@@ -729,7 +836,27 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     cuuint32_t box[4] = {64, HALF_X, TILE_Y, 1};
     rc = encode(&p.tmOut, act_dtype, 4, a.out.ptr, dims, str, box, 64);
   }
+  // staged epilogue (per-warp TMA store + TMA residual prefetch): N = 64, 16-bit output, shared bias
+  const bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad == 64 && (uintptr_t)a.out.ptr % 16 == 0 &&
+                           a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
+                           (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) && epi_staged_enabled();
+  if (!rc && want_staged) {
+    cuuint32_t box[4] = {64, HALF_X, 4, 1};
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)a.cout_pad, (cuuint64_t)a.out.W, (cuuint64_t)a.out.H, (cuuint64_t)a.batch};
+      cuuint64_t str[3] = {(cuuint64_t)a.out.pix_stride * esz, (cuuint64_t)a.out.W * a.out.pix_stride * esz,
+                           (cuuint64_t)a.out.H * a.out.W * a.out.pix_stride * esz};
+      rc = encode(&p.tmOut, act_dtype, 4, a.out.ptr, dims, str, box, 64);
+    }
+    if (!rc && a.has_res) {
+      cuuint64_t dims[4] = {(cuuint64_t)a.cout_pad, (cuuint64_t)a.res.W, (cuuint64_t)a.res.H, (cuuint64_t)a.batch};
+      cuuint64_t str[3] = {(cuuint64_t)a.res.pix_stride * esz, (cuuint64_t)a.res.W * a.res.pix_stride * esz,
+                           (cuuint64_t)a.res.H * a.res.W * a.res.pix_stride * esz};
+      rc = encode(&p.tmRes, act_dtype, 4, a.res.ptr, dims, str, box, 64);
+    }
+  }
   if (rc) { delete pl; return rc; }
+  p.epi_staged = want_staged ? 1 : 0;
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
   p.ksteps = ck / 16;
@@ -759,7 +886,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
   const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
   p.tma_out = want_tma_out ? 1 : 0;
-  p.stage_out_bytes = p.tma_out ? 2u * 16384u : 0u;
+  p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)EPI_WARPS * 4096u : 0u);
   const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
   const int nA = p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks);
   const size_t min_a = (p.patch1 ? 2 : 3) * (size_t)p.a_stage_bytes;   // a single-box stage already is a whole tile (per chunk)

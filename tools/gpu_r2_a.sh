@@ -6,7 +6,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 LIBDIR=arbitrary-hands-3d-reconstruction_b200/lib
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/a_smi.txt 2>&1
-# ---- 0. conv correctness: dual issuer alone (three boxes), then dual + single box
+# ---- 0. conv correctness: dual issuer alone (three boxes, direct epilogue), then + single box, then + staged epilogue
+export ACR_B200_EPI=0
 ACR_B200_P1=0 timeout 600 python -m pytest tests/test_gpu_conv.py -q -x > $OUT/a_conv_dual_p0.log 2>&1; DUAL_OK=$?
 if [ $DUAL_OK -ne 0 ]; then export ACR_B200_LIB=$PWD/$LIBDIR/libacr_b200_single.so; echo "DUAL ISSUER FAILED -> single" | tee $OUT/a_decision.txt; fi
 ACR_B200_P1=1 timeout 600 python -m pytest tests/test_gpu_conv.py -q -x > $OUT/a_conv_p1.log 2>&1; P1_OK=$?
@@ -15,17 +16,23 @@ if [ $P1_OK -ne 0 ]; then
   echo "P1 (base offset = kx) FAILED; zero base offset exit $?" | tee -a $OUT/a_decision.txt
   export ACR_B200_P1=0
 fi
-echo "dual_ok=$DUAL_OK p1_ok=$P1_OK lib=${ACR_B200_LIB:-default} P1=${ACR_B200_P1:-default}" | tee -a $OUT/a_decision.txt
+ACR_B200_EPI=1 timeout 600 python -m pytest tests/test_gpu_conv.py -q -x > $OUT/a_conv_epi.log 2>&1; EPI_OK=$?
+if [ $EPI_OK -eq 0 ]; then export ACR_B200_EPI=1; else echo "STAGED EPILOGUE FAILED" | tee -a $OUT/a_decision.txt; fi
+echo "dual_ok=$DUAL_OK p1_ok=$P1_OK epi_ok=$EPI_OK lib=${ACR_B200_LIB:-default} P1=${ACR_B200_P1:-default} EPI=$ACR_B200_EPI" | tee -a $OUT/a_decision.txt
 # ---- 1. per-layer A/B
 S1="64,64,3,1,64,0"; S2="64,64,3,1,128,0,64,4"; S3="64,64,3,1,64,1"; S4="64,64,3,1,128,1,64,4"
 LAYERS="$S1 $S2 $S3 $S4 128,128,3,1,32,1 256,256,3,1,16,1 64,64,3,1,128,0 64,256,1,1,128,1"
 for LIB in default single; do
   for P in 1 0; do
-    [ $P -eq 1 ] && [ $P1_OK -ne 0 ] && continue
-    [ $LIB = default ] && [ $DUAL_OK -ne 0 ] && continue
-    echo "== lib=$LIB P1=$P" >> $OUT/a_conv_ab.log
-    if [ $LIB = single ]; then L=$PWD/$LIBDIR/libacr_b200_single.so; else L=$PWD/$LIBDIR/libacr_b200.so; fi
-    ACR_B200_LIB=$L ACR_B200_P1=$P timeout 300 python tools/conv_bench.py $LAYERS >> $OUT/a_conv_ab.log 2>&1
+    for E in 1 0; do
+      [ $P -eq 1 ] && [ $P1_OK -ne 0 ] && continue
+      [ $E -eq 1 ] && [ $EPI_OK -ne 0 ] && continue
+      [ $LIB = default ] && [ $DUAL_OK -ne 0 ] && continue
+      [ $LIB = single ] && [ $P$E != 00 ] && [ $P$E != 11 ] && continue
+      echo "== lib=$LIB P1=$P EPI=$E" >> $OUT/a_conv_ab.log
+      if [ $LIB = single ]; then L=$PWD/$LIBDIR/libacr_b200_single.so; else L=$PWD/$LIBDIR/libacr_b200.so; fi
+      ACR_B200_LIB=$L ACR_B200_P1=$P ACR_B200_EPI=$E timeout 300 python tools/conv_bench.py $LAYERS >> $OUT/a_conv_ab.log 2>&1
+    done
   done
 done
 # ---- 2. everything
