@@ -104,6 +104,17 @@ def reorganize_results(outputs, img_paths, reorganize_idx):
     return results
 
 
+def save_results(image_folder, output_dir, results_dict):
+    """acr/utils.py:124-129: pickle the packaged results as
+    ``<output_dir>/<folder name>_hand<checkpoint file name>_<confidence threshold>.pkl``."""
+    import pickle
+    from acr.config import args
+    model_name = args().model_path.split('/')[-1]
+    path_name = image_folder.split('/')[-1]
+    with open(output_dir + f'/{path_name}_hand{model_name}_{args().centermap_conf_thresh}.pkl', 'wb') as f:
+        pickle.dump(results_dict, f)
+
+
 def img_preprocess(image, imgpath=None, input_size=512, single_img_input=False, bbox=None):
     """Drop-in for acr/utils.py:1315-1337 on the device: ``image`` is a BGR frame (numpy HxWx3 uint8, or a CUDA
     uint8 tensor HxWx3 / NxHxWx3); returns the reference's dict with ``image`` (uint8 RGB, white-padded to a

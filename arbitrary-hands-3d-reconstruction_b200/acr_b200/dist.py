@@ -42,6 +42,18 @@ def compact_gathered(gathered: torch.Tensor, counts: torch.Tensor) -> List[torch
     return [gathered[r, : int(n[r])] for r in range(gathered.shape[0])]
 
 
+def gather_layout(world: int, rows: int) -> dict:
+    """Byte layout of the symmetric gather allocation (include/acr_b200.h, acr_b200_gather): two slots of
+    verts[world][rows][778][3] fp32 + counts[world][8] int32, then flags[world] uint64."""
+    if rows % 2 or rows <= 0 or not 1 <= world <= 8:
+        raise ValueError("gather_layout: rows per rank must be even and positive, world in 1..8")
+    verts_bytes = world * rows * 778 * 3 * 4
+    counts_offset = (verts_bytes + 15) // 16 * 16
+    slot_bytes = (counts_offset + world * 32 + 255) // 256 * 256
+    return dict(counts_offset=counts_offset, slot_bytes=slot_bytes, flags_offset=2 * slot_bytes,
+                total_bytes=2 * slot_bytes + 256, verts_bytes=verts_bytes)
+
+
 class PeerVertexGather:
     """Vertex all-gather fused into the MANO kernel (``acr_b200_mano_forward_gather``, protocol in
     include/acr_b200.h).  One symmetric-memory allocation per rank holds TWO gather slots -- each
@@ -71,12 +83,9 @@ class PeerVertexGather:
         if self.rows % 2 or self.world > 8:
             raise ValueError("PeerVertexGather: rows per rank must be even and world <= 8")
         self.device = torch.device(device)
-        verts_bytes = self.world * self.rows * self.NV3 * 4
-        self.counts_offset = (verts_bytes + 15) // 16 * 16
-        self.slot_bytes = (self.counts_offset + self.world * 32 + 255) // 256 * 256
-        self.flags_offset = 2 * self.slot_bytes
-        total = self.flags_offset + 256
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        lay = gather_layout(self.world, self.rows)
+        self.counts_offset, self.slot_bytes, self.flags_offset = lay["counts_offset"], lay["slot_bytes"], lay["flags_offset"]
+        self.buf = symm_mem.empty(lay["total_bytes"], dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.local_state = torch.zeros(2, dtype=torch.int64, device=self.device)

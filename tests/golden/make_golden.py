@@ -24,9 +24,55 @@ REF = "/root/reference"
 
 def import_reference():
     """The harness itself lives in oracle/ref_harness.py (shared with the reference arm of bench.py)."""
+    sys.argv_saved = list(sys.argv)
     sys.path.insert(0, ROOT)
     from oracle import ref_harness
     return ref_harness.import_reference(REF, "make_golden")
+
+
+def pack_golden(torch, ref_utils):
+    """reorganize_results (acr/utils.py:1226-1271) + save_results (:124-129) of the reference on a seeded synthetic
+    batch: 7 hand rows over 3 images, two undetected rows, mixed hand types -> pack_golden.npz (inputs + the
+    reference's per-image / per-hand fp16 payloads, flattened) and the bytes layout of the pickle dump."""
+    import pickle
+    import tempfile
+    rng = np.random.default_rng(33)
+    N = 7
+    f = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    outputs = {"detection_flag_cache": torch.tensor([1, 1, 0, 1, 1, 0, 1], dtype=torch.bool),
+               "params_dict": {"cam": f(N, 3), "poses": f(N, 48), "betas": f(N, 10)},
+               "cam_trans": f(N, 3), "j3d": f(N, 21, 3), "verts": f(N, 778, 3) * 0.1, "pj2d": f(N, 21, 2),
+               "pj2d_org": f(N, 21, 2) * 300, "output_hand_type": torch.tensor([0, 0, 0, 1, 1, 1, 0], dtype=torch.int32)}
+    # rows surviving the detection filter keep their order: reorganize_idx / img_paths index the FILTERED rows
+    reorganize_idx = np.array([0, 2, 0, 1, 2])
+    img_paths = ["a.jpg", "c.jpg", "a.jpg", "b.jpg", "c.jpg"]
+    res = ref_utils.reorganize_results(outputs, img_paths, reorganize_idx)
+    flat = {"reorganize_idx": reorganize_idx, "img_paths": np.array(img_paths),
+            "detection_flag_cache": outputs["detection_flag_cache"].numpy(), "output_hand_type": outputs["output_hand_type"].numpy(),
+            "cam_trans": outputs["cam_trans"].numpy(), "j3d": outputs["j3d"].numpy(), "verts": outputs["verts"].numpy(),
+            "pj2d": outputs["pj2d"].numpy(), "pj2d_org": outputs["pj2d_org"].numpy()}
+    for k, v in outputs["params_dict"].items():
+        flat["pd_" + k] = v.numpy()
+    flat["result_keys"] = np.array(list(res.keys()))
+    for name, hands in res.items():
+        flat[f"res__{name}__n"] = len(hands)
+        for i, hd in enumerate(hands):
+            for k, v in hd.items():
+                flat[f"res__{name}__{i}__{k}"] = np.asarray(v)
+    # save_results: file name convention + pickle of the dict
+    import acr.config as ref_cfg
+    with tempfile.TemporaryDirectory() as d:
+        ref_utils.save_results("some/folder/clip7", d, res)
+        names = os.listdir(d)
+        assert len(names) == 1
+        flat["save_name"] = np.array(names[0])
+        flat["save_model_path"] = np.array(ref_cfg.args().model_path)
+        flat["save_conf"] = np.array(ref_cfg.args().centermap_conf_thresh)
+        with open(os.path.join(d, names[0]), "rb") as fh:
+            back = pickle.load(fh)
+        assert list(back.keys()) == list(res.keys())
+    np.savez_compressed(os.path.join(HERE, "pack_golden.npz"), **flat)
+    print("pack_golden:", {k: len(v) for k, v in res.items()}, str(flat["save_name"]))
 
 
 def main():
@@ -37,6 +83,8 @@ def main():
     import acr.utils as ref_utils
     from acr.mano_wrapper import MANOWrapper
     from mano.manolayer import batch_rodrigues
+    if "--only-pack" in sys.argv_saved:
+        return pack_golden(torch, ref_utils)
 
     # ------------------------------------------------------------------ rotations
     rng = np.random.default_rng(7)
@@ -197,6 +245,7 @@ def main():
              cam=out["params_dict"]["cam"].numpy(), verts=out["verts"].numpy(), j3d=out["j3d"].numpy(),
              pj2d_org=out["pj2d_org"].numpy(), reorganize_idx=out["reorganize_idx"].numpy())
     np.savez_compressed(os.path.join(HERE, "net_golden.npz"), **g)
+    pack_golden(torch, ref_utils)
     for k, v in g.items():
         print(k, getattr(v, "shape", v))
     print("backbone mean/std", g["backbone_mean"], g["backbone_std"])

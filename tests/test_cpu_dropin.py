@@ -119,3 +119,42 @@ def test_reorganize_results_packaging():
     assert res["a.jpg"][0]["hand_type"] == 0 and res["a.jpg"][1]["hand_type"] == 1
     assert res["b.jpg"][1]["verts"].dtype == np.float16 and res["b.jpg"][1]["verts"].shape == (778, 3)
     assert np.array_equal(res["b.jpg"][0]["poses"], out["params_dict"]["poses"][1].numpy().astype(np.float16))
+
+
+def test_reorganize_and_save_results_match_the_reference_golden(tmp_path):
+    """Result packaging: reorganize_results / save_results against pack_golden.npz, written by the
+    unmodified reference (acr/utils.py:1226-1271, 124-129) on a seeded batch with undetected rows and mixed hands."""
+    import os
+    import pickle
+
+    import numpy as np
+    import torch
+
+    from acr.config import args
+    from acr.utils import reorganize_results, save_results
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pack_golden.npz"))
+    outputs = {"detection_flag_cache": torch.from_numpy(g["detection_flag_cache"]),
+               "params_dict": {k: torch.from_numpy(g["pd_" + k]) for k in ("cam", "poses", "betas")},
+               "output_hand_type": torch.from_numpy(g["output_hand_type"])}
+    for k in ("cam_trans", "j3d", "verts", "pj2d", "pj2d_org"):
+        outputs[k] = torch.from_numpy(g[k])
+    res = reorganize_results(outputs, [str(p) for p in g["img_paths"]], g["reorganize_idx"])
+    assert list(res.keys()) == [str(k) for k in g["result_keys"]]
+    for name, hands in res.items():
+        assert len(hands) == int(g[f"res__{name}__n"])
+        for i, hd in enumerate(hands):
+            keys = sorted(k.split("__")[-1] for k in g.files if k.startswith(f"res__{name}__{i}__"))
+            assert sorted(hd.keys()) == keys
+            for k, v in hd.items():
+                ref = g[f"res__{name}__{i}__{k}"]
+                assert np.asarray(v).dtype == ref.dtype and np.array_equal(np.asarray(v), ref), (name, i, k)
+    old = args().model_path
+    args().model_path = str(g["save_model_path"])
+    try:
+        save_results("some/folder/clip7", str(tmp_path), res)
+    finally:
+        args().model_path = old
+    assert os.listdir(tmp_path) == [str(g["save_name"])]
+    with open(tmp_path / str(g["save_name"]), "rb") as f:
+        back = pickle.load(f)
+    assert list(back.keys()) == list(res.keys()) and np.array_equal(back["a.jpg"][0]["verts"], res["a.jpg"][0]["verts"])
