@@ -97,6 +97,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -192,7 +193,8 @@ struct ConvTcParams {
   CUtensorMap tmB;
   CUtensorMap tmOut;   // output as {C, W, H, B}, box {64, 8, 16, 1} (tma_out) or {64, 8, 4, 1} (epi_staged), 128B swizzle
   CUtensorMap tmRes;   // residual, box {64, 8, 4, 1}, 128B swizzle (epi_staged)
-  int epi_staged;      // N = 64, 16-bit output: every epilogue warp stages its 32 px x 128 B in shared memory, TMA in/out
+  int epi_staged;      // N % 64 == 0, 16-bit output: every epilogue warp stages 32 px x 128 B slabs in shared memory, TMA in/out
+  int epi_nb;          // staging buffers per epilogue warp (ring depth, 1..3)
   const float* bias;
   const void* res;
   void* out;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto tmem_full = [&](int b, int h) { return bres_bar + 8u * (1 + b * 2 + h); };
   auto tmem_empty = [&](int b, int h) { return bres_bar + 8u * (5 + b * 2 + h); };
   const uint32_t tmem_ptr_addr = bres_bar + 8u * 9;
-  auto res_full = [&](int w) { return bres_bar + 8u * (10 + w); };   // staged epilogue: residual box of warp w has landed
+  auto res_full = [&](int i) { return bres_bar + 8u * (10 + i); };   // staged epilogue: residual slab in buffer i % 3 of warp i / 3 has landed
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     mbar_init(bres_bar, 1);
     for (int b = 0; b < 2; ++b)
       for (int h = 0; h < 2; ++h) { mbar_init(tmem_full(b, h), 1); mbar_init(tmem_empty(b, h), EPI_WARPS / 2); }
-    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(res_full(w), 1);
+    for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(res_full(i), 1);
     fence_barrier_init();
     tma_prefetch_desc(&P.tmB);
     tma_prefetch_desc(&P.tmA[0]);
@@ -510,95 +512,113 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int it = 0;
     pdl_wait();   // residual / per-image bias reads and every output write wait for the previous kernel
     if (P.epi_staged && !DIAG) {
-      // ----------------------------------------------------------------- staged epilogue (N = 64, 16-bit output)
+      // ------------------------------------------------- staged epilogue (N multiple of 64, 16-bit output, shared bias)
       // Direct global accesses put every lane of a warp on its own 128-byte line (32 LSU wavefronts per instruction,
       // ncu: l1tex data pipe 77 % busy) and keep the residual's DRAM latency inside the per-tile critical path.
-      // Here every epilogue warp owns a 4 KB buffer = its 32 pixels (4 rows x 8 columns of the half tile) x 128 B in
-      // the 128B-swizzled layout of a TMA box {64, 8, 4}: the residual of the NEXT tile is fetched into it by a TMA
-      // load (asynchronous, one mbarrier per warp) as soon as the previous output has left, a thread reads / writes
-      // only its own row (conflict-free 16-byte accesses), and the result leaves with one TMA store per warp.
-      // Synchronisation is per warp only: __syncwarp + proxy fences, no CTA-wide barrier.
+      // Here the unit of work is a SLAB = the warp's 32 pixels (4 rows x 8 columns of the half tile) x 64 channels =
+      // 4 KB, the 128B-swizzled image of a TMA box {64, 8, 4}.  Every epilogue warp owns a ring of NB such buffers and
+      // walks the slabs of its tiles in order (slab k = (tile k / G, channels 64 (k % G) ..), G = N / 64):
+      //   * the residual of slab k is fetched into buffer k % NB by a TMA load (asynchronous, its own mbarrier) as soon
+      //     as the store that last used that buffer has finished reading it -- up to NB-1 slabs ahead, i.e. the DRAM
+      //     latency of the residual overlaps the processing of the previous slabs / the next tile's MMAs;
+      //   * a thread reads / rewrites only its own 128-byte row (conflict-free 16-byte accesses);
+      //   * the finished slab leaves with one TMA store.
+      // Synchronisation is per warp only: __syncwarp + proxy fences, bulk-group waits, no CTA-wide barrier.
       const int wi = warp - EPI_WARP0;
-      const uint32_t my_stage = stage_base + (uint32_t)wi * 4096u;
-      const uint32_t row = my_stage + (uint32_t)lane * 128u;
+      const int NB = P.epi_nb, G = P.npad >> 6;
+      const uint32_t my_stage = stage_base + (uint32_t)(wi * NB) * 4096u;
       const uint32_t sw = (uint32_t)(lane & 7);
       const bool has_res = P.has_res != 0;
-      uint32_t res_phase = 0;
-      auto tile_xy = [&](int tile, int& n, int& tx, int& ty) {
+      const int my_tiles = ((int)blockIdx.x < P.total_tiles) ? (P.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int total_slabs = my_tiles * G;
+      auto slab_xy = [&](int k, int& n, int& tx, int& ty, int& c0) {
+        const int tile = (int)blockIdx.x + (k / G) * (int)gridDim.x;
+        c0 = (k % G) * 64;
         n = tile / P.tiles_per_img;
         const int rem = tile % P.tiles_per_img;
         ty = (rem / P.tiles_x) * TILE_Y + 4 * q;
         tx = (rem % P.tiles_x) * TILE_X + h * HALF_X;
       };
-      if (has_res && (int)blockIdx.x < P.total_tiles && lane == 0) {
-        int n, tx, ty;
-        tile_xy(blockIdx.x, n, tx, ty);
-        mbar_expect_tx(res_full(wi), 4096u);
-        tma_load_4d(my_stage, &P.tmRes, res_full(wi), 0, tx, ty, n);
-      }
+      auto load_res = [&](int k) {    // lane 0 only
+        int n, tx, ty, c0;
+        slab_xy(k, n, tx, ty, c0);
+        const int b = k % NB;
+        mbar_expect_tx(res_full(wi * 3 + b), 4096u);
+        tma_load_4d(my_stage + (uint32_t)b * 4096u, &P.tmRes, res_full(wi * 3 + b), c0, tx, ty, n);
+      };
+      const int ahead = NB > 1 ? NB - 1 : 1;     // residual loads in flight beyond the slab being processed
+      if (has_res && lane == 0)
+        for (int k = 0; k < ahead && k < total_slabs; ++k) load_res(k);
+      int k = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
-        int n, tx, ty;
-        tile_xy(tile, n, tx, ty);
         mbar_wait(tmem_full(buf, h), use & 1u);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
-        uint32_t v[4][16];
+        for (int g = 0; g < G; ++g, ++k) {
+          int n, tx, ty, c0;
+          slab_xy(k, n, tx, ty, c0);
+          const int b = k % NB;
+          const uint32_t row = my_stage + (uint32_t)b * 4096u + (uint32_t)lane * 128u;
+          uint32_t v[4][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16(t_row + (uint32_t)(c * 16), v[c]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(buf, h));      // accumulator back to the issuer
-        if (has_res) {
-          mbar_wait(res_full(wi), res_phase);                  // this tile's residual box has landed
-          res_phase ^= 1u;
-        } else {
-          if (lane == 0) bulk_wait_read0();                    // the previous store has finished reading the buffer
+          for (int c = 0; c < 4; ++c) tmem_ld16(t_row + (uint32_t)(c0 + c * 16), v[c]);
+          tmem_ld_wait();
+          if (g == G - 1) {                                      // all TMEM reads of this tile done: accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(buf, h));
+          }
+          if (has_res) {
+            mbar_wait(res_full(wi * 3 + b), (uint32_t)(k / NB) & 1u);   // this slab's residual box has landed
+          } else {
+            if (lane == 0) {                                     // the store that last used this buffer has read it
+              if (NB == 1) bulk_wait_read0(); else if (NB == 2) bulk_wait_read<1>(); else bulk_wait_read<2>();
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + c * 16 + 4 * i);
+              f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
+              f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
+            }
+            const uint32_t a0 = row + ((((uint32_t)(2 * c)) ^ sw) << 4), a1 = row + ((((uint32_t)(2 * c + 1)) ^ sw) << 4);
+            if (has_res) {
+              float x[16];
+              unpack8<T>(lds128(a0), x);
+              unpack8<T>(lds128(a1), x + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += x[i];
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            sts128(a0, pack8<T>(f));
+            sts128(a1, pack8<T>(f + 8));
+          }
+          fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&P.tmOut, my_stage + (uint32_t)b * 4096u, c0, tx, ty, n);
+            bulk_commit();
+            const int kn = k + ahead;                            // next residual to fetch
+            if (has_res && kn < total_slabs) {
+              // its buffer was last used by the store of slab kn - NB: everything but the newest NB-1 groups (the
+              // store just committed included) must have finished reading shared memory
+              if (NB == 1) bulk_wait_read0(); else if (NB == 2) bulk_wait_read<1>(); else bulk_wait_read<1>();
+              load_res(kn);
+            }
+          }
           __syncwarp();
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 16 + 4 * i);
-            f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
-            f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
-          }
-          const uint32_t a0 = row + ((((uint32_t)(2 * c)) ^ sw) << 4), a1 = row + ((((uint32_t)(2 * c + 1)) ^ sw) << 4);
-          if (has_res) {
-            float x[16];
-            unpack8<T>(lds128(a0), x);
-            unpack8<T>(lds128(a1), x + 8);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += x[i];
-          }
-          if (P.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          sts128(a0, pack8<T>(f));
-          sts128(a1, pack8<T>(f + 8));
-        }
-        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA unit
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&P.tmOut, my_stage, 0, tx, ty, n);
-          bulk_commit();
-          const int next = tile + (int)gridDim.x;
-          if (has_res && next < P.total_tiles) {               // refill the buffer with the next tile's residual
-            bulk_wait_read0();
-            int n2, tx2, ty2;
-            tile_xy(next, n2, tx2, ty2);
-            mbar_expect_tx(res_full(wi), 4096u);
-            tma_load_4d(my_stage, &P.tmRes, res_full(wi), 0, tx2, ty2, n2);
-          }
-        }
-        __syncwarp();
       }
-      if (lane == 0) bulk_wait_all();                          // staging must outlive the stores
+      if (lane == 0) bulk_wait_all();                            // staging must outlive the stores
     } else
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
@@ -770,17 +790,20 @@ static bool tma_out_disabled() {
   return !(e && atoi(e) != 0);
 }
 
-// The single-box A operand (MODE_P1) is on by default; ACR_B200_P1=0 (read at plan creation) selects the three
-// kx-shifted boxes again (A/B timing).  ACR_B200_CONV_DIAG bit 16 zeroes the descriptor base offset (hardware probe).
+// The single-box A operand (MODE_P1) is an opt-in experiment (ACR_B200_P1=1, read at plan creation): on B200 neither
+// base offset = kx nor base offset = 0 gave correct results for descriptor starts inside a swizzle repeat
+// (tools/umma_shift_probe.cu isolates the hardware behaviour).  ACR_B200_CONV_DIAG bit 16 zeroes the base offset.
 static bool p1_enabled() {
   const char* e = getenv("ACR_B200_P1");
-  return !(e && atoi(e) == 0);
+  return e && atoi(e) != 0;
 }
 
-// ACR_B200_EPI=0 (read at plan creation) selects the direct-store epilogue for the N = 64 layers (A/B timing).
-static bool epi_staged_enabled() {
+// ACR_B200_EPI (read at plan creation): 0 = direct-store epilogue everywhere, 1 (default) = staged epilogue for the
+// layers with a residual (where it measured faster: the residual's DRAM latency leaves the critical path),
+// 2 = staged epilogue for every eligible layer (A/B timing).
+static int epi_staged_level() {
   const char* e = getenv("ACR_B200_EPI");
-  return !(e && atoi(e) == 0);
+  return e ? atoi(e) : 1;
 }
 
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
@@ -837,9 +860,24 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     rc = encode(&p.tmOut, act_dtype, 4, a.out.ptr, dims, str, box, 64);
   }
   // staged epilogue (per-warp TMA store + TMA residual prefetch): N = 64, 16-bit output, shared bias
-  const bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad == 64 && (uintptr_t)a.out.ptr % 16 == 0 &&
-                           a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
-                           (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) && epi_staged_enabled();
+  const int epi_level = epi_staged_level();
+  bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
+                     a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
+                     (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) &&
+                     (epi_level >= 2 || (epi_level == 1 && a.has_res));
+  // ring depth per epilogue warp: one buffer when a tile is one slab (the next tile's MMAs hide the residual fetch),
+  // otherwise as many (<= 3) as fit next to the operand stages
+  int epi_nb = 0;
+  if (want_staged) {
+    const size_t a_st = (size_t)(box_rows * box_cols) * ck * 2, b_blk = (size_t)a.cout_pad * ck * 2;
+    const size_t b_tot = (size_t)a.k * a.k * (a.cin_pad / ck) * b_blk;
+    const size_t min_a0 = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * a_st;
+    for (int nb = (a.cout_pad == 64 ? 1 : 3); nb >= 1 && !epi_nb; --nb) {
+      const size_t fx = 1024 + 1024 + 512 + (size_t)EPI_WARPS * nb * 4096;
+      if (b_tot + min_a0 + fx <= (size_t)SMEM_BUDGET || 4 * b_blk + min_a0 + fx <= (size_t)SMEM_BUDGET) epi_nb = nb;
+    }
+    if (!epi_nb) want_staged = false;
+  }
   if (!rc && want_staged) {
     cuuint32_t box[4] = {64, HALF_X, 4, 1};
     {
@@ -857,6 +895,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   }
   if (rc) { delete pl; return rc; }
   p.epi_staged = want_staged ? 1 : 0;
+  p.epi_nb = epi_nb;
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
   p.ksteps = ck / 16;
@@ -886,10 +925,11 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
   const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
   p.tma_out = want_tma_out ? 1 : 0;
-  p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)EPI_WARPS * 4096u : 0u);
+  p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)(EPI_WARPS * p.epi_nb) * 4096u : 0u);
   const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
   const int nA = p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks);
-  const size_t min_a = (p.patch1 ? 2 : 3) * (size_t)p.a_stage_bytes;   // a single-box stage already is a whole tile (per chunk)
+  // stages that must fit next to resident weights: a tile's worth of kx patches (3) for 3x3 stride-1 convs, 2 otherwise
+  const size_t min_a = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * (size_t)p.a_stage_bytes;
   p.b_resident = (b_total + min_a + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
   if (p.b_resident) {
     p.b_region_bytes = (uint32_t)((b_total + 1023) & ~(size_t)1023);

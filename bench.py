@@ -111,7 +111,7 @@ def pick_threads(fn, cores):
     import torch
     best, best_t, sweep = None, None, {}
     fn()                                    # warm caches / allocator once, not attributed to any thread count
-    for n in sorted({cores, 96, 64, 48, 32, 16, 8}, reverse=True):
+    for n in sorted({min(cores, 64), 48, 32, 24, 16, 8}, reverse=True):   # > 64 threads: minutes per pass on these convs
         if n > cores:
             continue
         torch.set_num_threads(n)

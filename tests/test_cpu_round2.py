@@ -132,7 +132,7 @@ def test_bench_traffic_stamp_and_thread_sweep(tmp_path, monkeypatch):
     assert t is None and alg is None and bid in note
     calls = []
     best, sweep = bench.pick_threads(lambda: calls.append(torch.get_num_threads()), 8)
-    assert best == 8 and list(sweep) == [8] and len(calls) == 2   # warm-up + one timed run per candidate
+    assert best == 8 and list(sweep) == [8] and len(calls) == 2, (best, sweep, calls)   # warm-up + one timed run per candidate
 
 
 def test_lazy_outputs_refuse_stale_maps():

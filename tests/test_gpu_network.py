@@ -249,10 +249,10 @@ def test_engine_cache_is_bounded_and_shares_weights(sd):
 def test_channel_slice_view_starts_at_its_offset(sd, image):
     """Engine.view of a channel slice (cam head = channels 112..114 of the 128-wide head tensor)."""
     from acr_b200.engine import Engine
-    eng = Engine(sd, 2, "cuda", torch.float16)
+    eng = Engine(sd, 2, "cuda", torch.float16, keep_extra=("l_cam_raw",))   # the 128-wide head tensor must outlive the run
     eng.run(image.cuda())
     torch.cuda.synchronize()
-    whole = eng.view("l_raw128" if "l_raw128" in eng.spec.tensors else eng.spec.tensors["l_cam_raw"].base)
+    whole = eng.view(eng.spec.tensors["l_cam_raw"].base)
     assert torch.equal(eng.view("l_cam_raw")[..., :3], whole[..., 112:115])
     assert torch.equal(eng.map_nchw("l_cam_raw"), whole[..., 112:115].permute(0, 3, 1, 2).float())
     assert float(eng.map_nchw("l_cam_raw")[:, 0].min()) > 0.0          # channel 0 went through 1.1**x
