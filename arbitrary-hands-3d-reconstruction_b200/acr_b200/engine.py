@@ -115,7 +115,8 @@ class Engine:
         self.npw = np.float32 if self.f32 else np.uint16      # numpy type of one packed weight
         self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
         self.head_only = head_only
-        self.spec: NetSpec = build_acr_spec(input_size)
+        import os
+        self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0")
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)
         self.debug_ref_conv = debug_ref_conv or self.f32
@@ -331,6 +332,20 @@ class Engine:
                     o.cin_pad = o.cout_pad = 64
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, 64, pair=True)
                     o.shift[0] = 4      # ACR_CONV_XPAIR: side taps are 32x32 corners of the 64x64 block
+                elif a.get("merged"):
+                    # convs of identical geometry on the same input: weights / biases concatenated along cout
+                    each = a["merged"]
+                    wps, bs = [], []
+                    for wk, bk in zip(a["w"], a["bn"]):
+                        tmp = _Blob()
+                        self._pack_conv(sd, tmp, wk, bk, a["bias"], o.cin_pad, each)
+                        raw = tmp.tobytes()
+                        nw = each * a["k"] * a["k"] * o.cin_pad * np.dtype(self.npw).itemsize
+                        wps.append(np.frombuffer(raw[:nw], self.npw))
+                        boff = _rup(nw, 256)
+                        bs.append(np.frombuffer(raw[boff: boff + each * 4], np.float32))
+                    o.w_offset[0] = blob.add(np.concatenate(wps))
+                    o.w_offset[1] = blob.add(np.concatenate(bs))
                 else:
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
                     if a.get("pow11"):

@@ -87,6 +87,33 @@ class NetSpec:
                                 residual=residual is not None, pow11=pow11)))
         return y
 
+    def reg_conv(self, wkey: str, bnkey: Optional[str], cout: int, cin: int, k: int, bias: bool) -> None:
+        """Parameter registration of one conv (+BN), in the position of the registry where it is called (the seeded
+        synthetic weights and the golden fixtures depend on the registration ORDER, which follows the reference's
+        module construction order)."""
+        self._reg(wkey + ".weight", (cout, cin, k, k), "conv_w")
+        if bias:
+            self._reg(wkey + ".bias", (cout,), "conv_b")
+        if bnkey:
+            self._reg_bn(bnkey, cout)
+
+    def conv_merged(self, x: Tensor, keys: List[Tuple[str, Optional[str]]], cout: int, k: int, s: int = 1,
+                    relu: bool = False, bias: bool = False, hint: str = "merged") -> List[Tensor]:
+        """Several convs of identical geometry that read the SAME input, run as ONE conv with their output
+        channels concatenated (one pass over the input, N = len(keys) * cout per MMA instead of len(keys)
+        launches of N = cout).  Returns the channel slices of the wide output, one per original conv.  The
+        parameters are NOT registered here: the caller registers them with reg_conv where the reference builds them."""
+        assert cout % 16 == 0
+        wide = self._t(cout * len(keys), x.H // s, x.W // s, hint)
+        slices = []
+        for i, (wkey, _) in enumerate(keys):
+            t = Tensor(f"{wide.name}_s{i}", cout, wide.H, wide.W, "act", base=wide, c_off=i * cout)
+            self.tensors[t.name] = t
+            slices.append(t)
+        self.ops.append(Op("conv", wide, [x], dict(w=[w for w, _ in keys], bn=[b for _, b in keys], bias=bias, k=k, s=s,
+                                                   relu=relu, residual=False, pow11=False, merged=cout)))
+        return slices
+
     def fuse(self, terms: List[Tuple[Tensor, int]], relu=True, out: Optional[Tensor] = None) -> Tensor:
         t0 = terms[0][0]
         H, W = t0.H << terms[0][1], t0.W << terms[0][1]
@@ -150,8 +177,9 @@ def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bo
     return outs
 
 
-def build_acr_spec(input_size: int = 512) -> NetSpec:
-    """Full ACR network for one image of ``input_size`` x ``input_size``."""
+def build_acr_spec(input_size: int = 512, merge_stems: bool = True) -> NetSpec:
+    """Full ACR network for one image of ``input_size`` x ``input_size``.  ``merge_stems=False`` keeps the eight
+    head stem convs as eight launches (A/B timing of the merged form)."""
     g = NetSpec()
     S = input_size
     img = Tensor("image", 3, S, S, "u8")
@@ -207,6 +235,13 @@ def build_acr_spec(input_size: int = 512) -> NetSpec:
     # ---- global heads (acr/model.py:68-101, 288-313): 8 stacks on the 34-ch map
     heads = {}
     raw128 = {}
+    # the eight head stems (conv3x3 s2 34->64 + BN + ReLU, acr/model.py:288-296) all read the coord-concat map: they run
+    # as two merged convs of N = 4 x 64 (one per side), each a single pass over the 128x128x34 input
+    stems = {}
+    for side in ("l", "r") if merge_stems else ():
+        keys = [(f"{side}_final_layers.{idx}.0.0", f"{side}_final_layers.{idx}.0.1") for idx in (1, 2, 3, 4)]
+        for idx, t in zip((1, 2, 3, 4), g.conv_merged(xcat, keys, 64, 3, s=2, relu=True, bias=True, hint=f"{side}_stems")):
+            stems[(side, idx)] = t
     for side in ("l", "r"):
         # params (106) and cam (3, scale channel through 1.1**x) heads write 16-bit slices [0,112) and
         # [112,128) of one 128-channel tensor: the input of the folded contact_layers[4|5] conv
@@ -217,7 +252,11 @@ def build_acr_spec(input_size: int = 512) -> NetSpec:
             g.tensors[t.name] = t
         for idx, (nm, co) in {1: ("params", 106), 2: ("center", 1), 3: ("cam", 3), 4: ("prior", 106)}.items():
             p = f"{side}_final_layers.{idx}"
-            h = g.conv(xcat, p + ".0.0", p + ".0.1", 64, 3, s=2, relu=True, bias=True)
+            if merge_stems:
+                g.reg_conv(p + ".0.0", p + ".0.1", 64, xcat.C, 3, bias=True)    # runs inside the merged stem conv above
+                h = stems[(side, idx)]
+            else:
+                h = g.conv(xcat, p + ".0.0", p + ".0.1", 64, 3, s=2, relu=True, bias=True)
             for blk in range(2):
                 h = _basic_block(g, h, f"{p}.1.{blk}.0", 64)
             if nm in slices:

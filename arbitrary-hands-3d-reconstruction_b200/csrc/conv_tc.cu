@@ -231,9 +231,13 @@ constexpr int MODE_PATCH = 1, MODE_RESIDENT = 2, MODE_XPAIR = 4;
 // MODE_P1 (with MODE_PATCH, CK = 64): the whole haloed input patch of a super-tile is ONE TMA box {64, 24, 18} per channel
 // chunk (x0-1 .. x0+22, y0-1 .. y0+16; the row pitch of 24 pixels keeps every image row on a swizzle-atom boundary).
 // The nine taps are nine UMMA descriptors into it: ky moves the start by whole image rows, kx by single pixels --
-// a start address that is NOT aligned to the 1024-byte swizzle repeat, which the descriptor's base-offset field
-// ((start >> 7) & 7 = kx) declares.  One box instead of three: a third of the TMA issues, half the L2 -> smem
-// bytes, half the shared memory per tile (so a whole tile of look-ahead fits next to resident weights).
+// a start address that is NOT aligned to the 1024-byte swizzle repeat.  tools/umma_shift_probe.cu established how
+// the tensor core treats that (B200, profiles/r2_umma_shift_probe.log): the 128-byte swizzle is a function of the
+// ABSOLUTE shared-memory address bits (chunk ^= (addr >> 7) & 7), exactly like the TMA unit wrote the box, so any
+// 128-byte-aligned start works with base offset 0; a non-zero base-offset field XORs the chunk order once more (it is
+// for layouts whose swizzle pattern is relative to the tile, not ours).  One box instead of three: a third of the
+// TMA issues, half the L2 -> smem bytes, half the shared memory per tile (a whole tile of look-ahead fits next to
+// resident weights).
 constexpr int MODE_P1 = 16;
 constexpr int P1_PITCH = 24;   // pixels per image row of the single box
 // MODE_DIAG: diagnostic instances (tools/conv_bench.py, ACR_B200_CONV_DIAG=bits): 1 = the issuer skips the MMAs,
@@ -444,8 +448,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (RESIDENT) b_lo = b_lo_base + (uint32_t)((ky * 3 + kx) * cchunks + cc) * b_block16;
                 else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
                 const uint32_t first = (ky == 0 && i == 0) ? (cc != 0 ? 1u : 0u) : 1u;
-                // base offset = swizzle phase of the first row = kx (rows are 128 B, every image row starts a repeat)
-                const uint32_t hi1 = (SBO1 >> 4) | (1u << 14) | ((P.debug & 16) ? 0u : ((uint32_t)kx << 17)) | (Cfg::kLayout << 29);
+                // base offset 0: the swizzle phase comes from the absolute address (see MODE_P1 above)
+                const uint32_t hi1 = (SBO1 >> 4) | (1u << 14) | (Cfg::kLayout << 29);
                 issue_hi(d0, a_lo + (uint32_t)(ky * P1_PITCH + kx) * (Cfg::kRowBytes >> 4), hi1, b_lo, first, kx);
                 if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
               }
@@ -790,16 +794,16 @@ static bool tma_out_disabled() {
   return !(e && atoi(e) != 0);
 }
 
-// The single-box A operand (MODE_P1) is an opt-in experiment (ACR_B200_P1=1, read at plan creation): on B200 neither
-// base offset = kx nor base offset = 0 gave correct results for descriptor starts inside a swizzle repeat
-// (tools/umma_shift_probe.cu isolates the hardware behaviour).  ACR_B200_CONV_DIAG bit 16 zeroes the base offset.
+// The single-box A operand (MODE_P1) is on by default; ACR_B200_P1=0 (read at plan creation) selects the three
+// kx-shifted boxes again (A/B timing).
 static bool p1_enabled() {
   const char* e = getenv("ACR_B200_P1");
-  return e && atoi(e) != 0;
+  return !(e && atoi(e) == 0);
 }
 
-// ACR_B200_EPI (read at plan creation): 0 = direct-store epilogue everywhere, 1 (default) = staged epilogue for the
-// layers with a residual (where it measured faster: the residual's DRAM latency leaves the critical path),
+// ACR_B200_EPI (read at plan creation): 0 = direct-store epilogue everywhere, 1 (default) = staged epilogue where it
+// measured faster (profiles/r2_conv_ab_epilogue.log): every layer with a residual -- its DRAM latency leaves the
+// critical path: 64->256 1x1 + residual 1123 -> 730 us = the HBM copy rate -- and the wide 1x1 convs,
 // 2 = staged epilogue for every eligible layer (A/B timing).
 static int epi_staged_level() {
   const char* e = getenv("ACR_B200_EPI");
@@ -864,7 +868,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
                      a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
                      (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) &&
-                     (epi_level >= 2 || (epi_level == 1 && a.has_res));
+                     (epi_level >= 2 || (epi_level == 1 && (a.has_res || (a.k == 1 && a.cout_pad >= 256))));
   // ring depth per epilogue warp: one buffer when a tile is one slab (the next tile's MMAs hide the residual fetch),
   // otherwise as many (<= 3) as fit next to the operand stages
   int epi_nb = 0;
@@ -975,7 +979,7 @@ template <int CK, typename T>
 static int launch_mode(const ConvTcPlan* pl, cudaStream_t st) {
   const int mode = (pl->p.patch_mode ? MODE_PATCH : 0) | (pl->p.b_resident ? MODE_RESIDENT : 0);
   if (CK == 64 && pl->p.patch1) {
-    if (pl->p.debug & ~16) { set_error("conv_tc: diagnostic instances exist for the three-box form only (ACR_B200_P1=0)"); return ACR_B200_EINVAL; }
+    if (pl->p.debug) { set_error("conv_tc: diagnostic instances exist for the three-box form only (ACR_B200_P1=0)"); return ACR_B200_EINVAL; }
     if (pl->p.xpair) {
       if (!pl->p.b_resident) { set_error("conv_tc: x-paired conv needs resident weights"); return ACR_B200_EINVAL; }
       return launch_inst<64, T, MODE_PATCH | MODE_RESIDENT | MODE_XPAIR | MODE_P1>(pl, st);

@@ -25,8 +25,15 @@ def sd():
 
 @pytest.fixture(scope="module")
 def image():
+    # one frame: the sweep re-computes every op on the CPU, and every kernel works per image (the batch dimension is
+    # covered by tests/test_gpu_network.py::test_full_batch_256_is_batch_invariant)
     gi = torch.Generator().manual_seed(123)
-    return torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
+    return torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)[1:]
+
+
+def _pare(eng, s):
+    """(B,106) contact + shape offsets of side s: the part head packs them densely (106 floats per image)."""
+    return eng.view(f"{s}_pare").float().cpu().reshape(-1)[: eng.batch * 106].view(eng.batch, 106)
 
 
 def sweep(eng, sd, image, tol):
@@ -47,9 +54,14 @@ def sweep(eng, sd, image, tol):
                 s = a["fold_side"]
                 raw = eng.view(r["ins"][0]).float().cpu()                      # (B,64,64,128): params 0..105, cam 112..114
                 prm, cam = raw[..., :106].permute(0, 3, 1, 2), raw[..., 112:115].permute(0, 3, 1, 2)
-                pare = eng.view(f"{s}_pare").float().cpu().reshape(raw.shape[0], -1)[:, :106]
+                pare = _pare(eng, s)
                 checks.append((f"contact_layers[{'4' if s == 'l' else '5'}] folded 218->109", get(r["out"]),
                                op_ref.final_params(prm, cam, pare, sdf, s)))
+            elif a.get("merged"):          # convs on the same input run as one wide conv: every slice against its own conv
+                x, got, each = get(r["ins"][0]), get(r["out"]), a["merged"]
+                for j, (wk, bk) in enumerate(zip(a["w"], a["bn"])):
+                    checks.append((f"conv {wk} (slice {j} of a merged conv)", got[:, j * each:(j + 1) * each],
+                                   op_ref.conv_bn_act(x, sdf, wk, bk, a["s"], a["relu"])))
             else:
                 res = get(r["ins"][1]) if a["residual"] else None
                 exp = op_ref.conv_bn_act(get(r["ins"][0]), sdf, a["w"], a["bn"], a["s"], a["relu"], res, a["pow11"])
@@ -75,7 +87,7 @@ def sweep(eng, sd, image, tol):
             checks.append(("attention pooling (softmax over HW x features)", pooled,
                            op_ref.attention_pool(get(pool_in[0]), get(pool_in[1]))))
             for s in "lr":
-                pare = eng.view(f"{s}_pare").float().cpu().reshape(B, -1)[:, :106]
+                pare = _pare(eng, s)
                 checks.append((f"part head {s}: LocallyConnected2d + Linear", pare, op_ref.part_offsets(pooled, sdf, s)))
         else:
             raise AssertionError(f"op kind {kind} has no teacher-forced check")
@@ -116,10 +128,10 @@ def test_heads_only_plan_teacher_forced(sd, image):
     from acr_b200.engine import Engine
     from oracle import net_ref
     torch.set_num_threads(os.cpu_count())
-    x = net_ref._Net(sd).backbone(image[:1])
+    x = net_ref._Net(sd).backbone(image)
     eng = Engine(sd, 1, "cuda", torch.bfloat16, reuse_memory=False, head_only=True)
     eng.run_heads(x.cuda())
     torch.cuda.synchronize()
-    rows = sweep(eng, sd, image[:1], TOL[torch.bfloat16])
+    rows = sweep(eng, sd, image, TOL[torch.bfloat16])
     bad = [(i, l, e) for i, l, e in rows if not e <= TOL[torch.bfloat16]]
     assert len(rows) >= 55 and not bad, bad[:8]
