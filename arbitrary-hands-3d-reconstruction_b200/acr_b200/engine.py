@@ -6,6 +6,7 @@ single C call (``acr_b200_plan_run``) that issues every kernel of the backbone +
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -115,7 +116,6 @@ class Engine:
         self.npw = np.float32 if self.f32 else np.uint16      # numpy type of one packed weight
         self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
         self.head_only = head_only
-        import os
         self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0")
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)
@@ -127,11 +127,20 @@ class Engine:
 
     # ------------------------------------------------------------------ weights
     def _pack_conv(self, sd, blob: _Blob, wkey: str, bnkey: Optional[str], has_bias: bool, cin_pad: int,
-                   cout_pad: int, pair: bool = False) -> Tuple[int, int]:
+                   cout_pad: int, pair: bool = False, s2x: bool = False) -> Tuple[int, int]:
         w = np.ascontiguousarray(sd[wkey + ".weight"], np.float32)
         cb = np.ascontiguousarray(sd[wkey + ".bias"], np.float32) if has_bias else None
         bn = [np.ascontiguousarray(sd[f"{bnkey}.{n}"], np.float32) for n in
               ("weight", "bias", "running_mean", "running_var")] if bnkey else [None] * 4
+        if s2x:
+            # stride-2 conv of a dense 32-channel tensor read as x-pairs (row = even pixel's channels | odd pixel's): tap
+            # (ky,kx) reads the even half for kx = 1 and the odd half for kx = 0 (pair ox-1) / kx = 2 (pair ox)
+            co, ci = w.shape[:2]
+            w2 = np.zeros((co, 2 * ci, 3, 3), np.float32)
+            for kx in range(3):
+                off = 0 if kx == 1 else ci
+                w2[:, off:off + ci, :, kx] = w[:, :, :, kx]
+            w = w2
         if pair:
             # x-paired grid: channel index = dx*32 + c.  Output pixel x_out = 2j+dxo reads input pixel
             # x_in = 2(j+pt-1)+dxi through the original tap kx = x_in - x_out + 1 (zero block if outside 0..2)
@@ -277,6 +286,16 @@ class Engine:
                 ct.C, ct.W, ct.pix_stride = 64, t.W // 2, 64
             return ct
 
+        def s2x_able(r) -> bool:
+            """3x3 stride-2 convs of a DENSE 32-channel tensor read it as x-pairs (H, W/2, 64): two boxes per tile with
+            128-byte rows instead of nine 64-byte-row boxes of four parity views (csrc/conv_tc.cu MODE_S2X)."""
+            a = r.get("attrs", {})
+            if self.f32 or r["kind"] != L.OP_CONV or a.get("k") != 3 or a.get("s") != 2 or a.get("merged") or "stem" in a:
+                return False
+            x, y = r["ins"][0], r["out"]
+            return (x.C == 32 and x.base is None and x.dtype == "act" and x.W % 32 == 0 and y.H % 16 == 0 and y.W % 16 == 0
+                    and os.environ.get("ACR_B200_S2X", "1") != "0")
+
         def pairable(r) -> bool:
             """3x3 stride-1 32->32 convs on dense tensors run as 64->64 convs on the x-paired grid: same
             bytes in memory, but 128-byte operand rows (SWIZZLE_128B) instead of 64-byte ones."""
@@ -293,10 +312,11 @@ class Engine:
             o = cops[i]
             o.kind = r["kind"]
             pair = pairable(r)
+            s2x = s2x_able(r)
             o.out = ctensor(r["out"], pair)
             o.n_in = len(r["ins"])
             for j, t in enumerate(r["ins"]):
-                o.in_[j] = ctensor(t, pair)
+                o.in_[j] = ctensor(t, pair or (s2x and j == 0))
             for j, t in enumerate(r.get("aux", [])):
                 o.aux[j] = ctensor(t)
             a = r.get("attrs", {})
@@ -328,6 +348,10 @@ class Engine:
                     o.cin_pad = 128
                     o.w_offset[0] = self._pack_raw(blob, weff, o.cin_pad, o.cout_pad)
                     o.shift[0] = 1      # ACR_CONV_BIAS_PER_IMAGE (aux[0] = bias_img from the part head)
+                elif s2x:
+                    o.cin_pad = 64
+                    o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, o.cout_pad, s2x=True)
+                    o.shift[0] = 8      # ACR_CONV_S2X
                 elif pair:
                     o.cin_pad = o.cout_pad = 64
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, 64, pair=True)

@@ -207,7 +207,8 @@ struct ConvTcParams {
   int vec256;   // output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int ksteps;   // k16 steps of a chunk that hold real channels (the rest are TMA zero fill: skipped)
   int patch_mode, b_resident, SA, SB;
-  int patch1;   // MODE_P1: ONE 24-wide haloed box per channel chunk, kx shifts through the descriptor base offset
+  int patch1;   // MODE_P1: ONE 24-wide haloed box per channel chunk, kx shifts = unaligned descriptor starts
+  int s2x;      // MODE_S2X: 3x3 stride-2 conv of a dense 32-channel tensor read as x-pairs: two row-parity boxes per tile
   uint32_t a_stage_bytes, b_block_bytes, b_region_bytes;
   int tmem_cols, acc_stride, nbuf;
   int tiles_x, tiles_per_img, total_tiles, Ho, Wo, out_stride, res_stride;
@@ -240,6 +241,15 @@ constexpr int MODE_PATCH = 1, MODE_RESIDENT = 2, MODE_XPAIR = 4;
 // resident weights).
 constexpr int MODE_P1 = 16;
 constexpr int P1_PITCH = 24;   // pixels per image row of the single box
+// MODE_S2X (CK = 64): 3x3 STRIDE-2 conv whose input is a dense 32-channel tensor, viewed as (H, W/2, 64): one 128-byte
+// row = an even pixel's 32 channels followed by its odd neighbour's.  Output pixel (oy, ox) reads input columns
+// 2ox-1, 2ox, 2ox+1 = [pair ox-1, odd half], [pair ox, even half], [pair ox, odd half] and rows 2oy-1, 2oy, 2oy+1 =
+// odd-row view row oy-1, even-row view row oy, odd-row view row oy+1.  So a 16x16 output tile needs TWO boxes
+// {64, 24 pair columns from x0-1, 17 rows} (even rows from y0, odd rows from y0-1) instead of nine 64-byte-row
+// boxes of four parity views: the nine taps are descriptor starts inside them (row offset 0/1, pair-column offset
+// 0/1 = an unaligned start, K half 0/1 = k-steps {0,1} or {2,3}).  The packed weights carry the 32 input channels
+// of tap (ky,kx) at K offset 32*(kx != 1) (engine._pack_conv(s2x=True)).
+constexpr int MODE_S2X = 32;
 // MODE_DIAG: diagnostic instances (tools/conv_bench.py, ACR_B200_CONV_DIAG=bits): 1 = the issuer skips the MMAs,
 // 2 = the epilogue only recycles the accumulator, 4 = the epilogue reads TMEM but skips math and stores.  Timing
 // floors of each warp role; never launched by the product path (debug == 0).
@@ -249,8 +259,9 @@ template <int CK, typename T, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using Cfg = SwizzleCfg<CK>;
   constexpr bool PATCH = (MODE & MODE_PATCH) != 0, RESIDENT = (MODE & MODE_RESIDENT) != 0, XPAIR = (MODE & MODE_XPAIR) != 0;
-  constexpr bool P1 = (MODE & MODE_P1) != 0;
+  constexpr bool P1 = (MODE & MODE_P1) != 0, S2X = (MODE & MODE_S2X) != 0;
   static_assert(!P1 || (PATCH && CK == 64), "the single-box form exists for CK = 64 patch convs");
+  static_assert(!S2X || (!PATCH && !P1 && !XPAIR && CK == 64), "the x-paired stride-2 form is a CK = 64 mode of its own");
   constexpr bool DIAG = (MODE & MODE_DIAG) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nA = P.patch1 ? P.cchunks : (P.patch_mode ? P.cchunks * 3 : P.taps * P.cchunks);  // A loads per super-tile
+  const int nA = P.s2x ? 2 : (P.patch1 ? P.cchunks : (P.patch_mode ? P.cchunks * 3 : P.taps * P.cchunks));  // A loads per super-tile
   const int nsub = P.patch1 ? 9 : (P.patch_mode ? 3 : 1);                                     // taps served by one A load
   const int nbuf = P.nbuf;
 
@@ -323,7 +334,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int y0 = (rem / P.tiles_x) * TILE_Y, x0 = (rem % P.tiles_x) * TILE_X;
         for (int a = 0; a < nA; ++a) {
           int cc, view = 0, dy = 0, dx = 0, tap0;
-          if (P.patch1) {               // one 18x24 box per channel chunk: rows y0-1 .. y0+16, columns x0-1 .. x0+22
+          int nsub_a = nsub;
+          if (P.s2x) {                  // a = row parity: even rows from y0 (taps ky=1), odd rows from y0-1 (ky=0,2)
+            cc = 0; view = a; dy = a ? -1 : 0; dx = -1; tap0 = 0; nsub_a = a ? 6 : 3;
+          } else if (P.patch1) {        // one 18x24 box per channel chunk: rows y0-1 .. y0+16, columns x0-1 .. x0+22
             cc = a; dy = -1; dx = -1; tap0 = 0;
           } else if (P.patch_mode) {    // one 18x16 box per (channel chunk, kx); rows y0-1 .. y0+16
             cc = a / 3; const int kx = patch_kx(a % 3, P.xpair);
@@ -348,9 +362,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           __syncwarp();
           if (++sa == SA) { sa = 0; pha ^= 1u; }
           if (!P.b_resident) {
-            for (int sub = 0; sub < nsub; ++sub) {
-              // weight block order = the issuer's tap order (single box: ky-major, kx 1,0,2 for x-paired convs)
-              const int tap = P.patch1 ? (sub / 3) * 3 + patch_kx(sub % 3, P.xpair) : (P.patch_mode ? sub * 3 + tap0 : tap0);
+            for (int sub = 0; sub < nsub_a; ++sub) {
+              // weight block order = the issuer's tap order (single box: ky-major, kx 1,0,2 for x-paired convs;
+              // stride-2 pairs: ky=1 with the even-row box, then ky=0 and ky=2 with the odd-row box)
+              const int tap = P.s2x ? (a == 0 ? 3 + sub : (sub < 3 ? sub : 3 + sub))
+                                    : (P.patch1 ? (sub / 3) * 3 + patch_kx(sub % 3, P.xpair) : (P.patch_mode ? sub * 3 + tap0 : tap0));
               mbar_wait(emptyB(sb), phb ^ 1u);
               if (elect_one_sync()) {
                 mbar_expect_tx(fullB(sb), P.b_block_bytes);
@@ -432,7 +448,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int hh = 0; hh < NH; ++hh) mbar_wait(tmem_empty(buf, h0 + hh), (use & 1u) ^ 1u);  // epilogue drained the accumulator(s)
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 + h0) * acc_stride;
-        if (P1) {
+        if (S2X) {
+          // two A stages per tile (even-row box, odd-row box); tap (ky,kx): row offset (ky == 2), pair-column offset
+          // (kx != 0), K half (kx != 1) -> k-steps {0,1} or {2,3} of the 64-wide row, same k-steps of the weight block
+          constexpr uint32_t SBO1 = P1_PITCH * Cfg::kRowBytes;
+          const uint32_t hi1 = (SBO1 >> 4) | (1u << 14) | (Cfg::kLayout << 29);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            mbar_wait(fullA(sa), pha);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo_base + (uint32_t)sa * a_stage16;
+#pragma unroll
+            for (int t9 = 0; t9 < 6; ++t9) {
+              if (v == 0 && t9 >= 3) continue;
+              const int ky = v == 0 ? 1 : (t9 < 3 ? 0 : 2), kx = t9 % 3;
+              uint32_t b_lo;
+              if (RESIDENT) b_lo = b_lo_base + (uint32_t)(ky * 3 + kx) * b_block16;
+              else { mbar_wait(fullB(sb), phb); tc_fence_after(); b_lo = b_lo_base + (uint32_t)sb * b_block16; }
+              const uint32_t a_tap = a_lo + (uint32_t)((ky == 2 ? P1_PITCH : 0) + (kx != 0 ? 1 : 0)) * (Cfg::kRowBytes >> 4);
+              const int ks0 = kx == 1 ? 0 : 2;
+              if (!(DIAG && (P.debug & 1))) {
+#pragma unroll
+                for (int ks = ks0; ks < ks0 + 2; ++ks) {
+                  const uint32_t f = (v == 0 && t9 == 0 && ks == ks0) ? 0u : 1u;
+#pragma unroll
+                  for (int hh = 0; hh < NH; ++hh)
+                    umma_f16_lohi(d0 + hh * acc_stride, a_tap + hh * (Cfg::kAtom >> 4) + ks * 2, hi1, b_lo + ks * 2, hi_b, idesc, f);
+                }
+              }
+              if (!RESIDENT) { umma_commit(emptyB(sb)); if (++sb == SB) { sb = 0; phb ^= 1u; } }
+            }
+            umma_commit(emptyA(sa));
+            if (++sa == SA) { sa = 0; pha ^= 1u; }
+          }
+        } else if (P1) {
           // one A stage per channel chunk; tap (ky,kx) starts (ky * 24 + kx) pixels into it (+ 8 for the right half)
           constexpr uint32_t SBO1 = P1_PITCH * Cfg::kRowBytes;
           for (int cc = 0; cc < cchunks; ++cc) {
@@ -802,9 +851,10 @@ static bool p1_enabled() {
 }
 
 // ACR_B200_EPI (read at plan creation): 0 = direct-store epilogue everywhere, 1 (default) = staged epilogue where it
-// measured faster (profiles/r2_conv_ab_epilogue.log): every layer with a residual -- its DRAM latency leaves the
-// critical path: 64->256 1x1 + residual 1123 -> 730 us = the HBM copy rate -- and the wide 1x1 convs,
-// 2 = staged epilogue for every eligible layer (A/B timing).
+// measured faster (profiles/r2_conv_ab_epilogue.log, r2_conv_ab_singlebox.log): every layer with a residual -- its
+// DRAM latency leaves the critical path: 64->256 1x1 + residual 1123 -> 730 us = the HBM copy rate --, every N = 64
+// layer (with the single-box operand there is room for the staging buffers next to a whole tile of look-ahead:
+// x-paired 32->32 114 -> 101 us) and the wide convs of narrow inputs, 2 = every eligible layer (A/B timing).
 static int epi_staged_level() {
   const char* e = getenv("ACR_B200_EPI");
   return e ? atoi(e) : 1;
@@ -818,18 +868,32 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ACR_CHECK_ARG(!(a.k == 1 && a.stride != 1), "conv_tc: 1x1 stride-2 unsupported");
   ACR_CHECK_ARG(!a.xpair || (a.k == 3 && a.stride == 1 && a.cin_pad == 64 && a.cout_pad == 64 && a.in.pix_stride >= 64),
                 "conv_tc: the x-paired form is a 3x3 stride-1 64->64 conv");
+  ACR_CHECK_ARG(!a.s2x || (a.k == 3 && a.stride == 2 && a.cin_pad == 64 && a.in.pix_stride == 64 && a.in.C == 64 && !a.xpair &&
+                           a.in.H == 2 * a.out.H && a.in.W == a.out.W),
+                "conv_tc: the x-paired stride-2 form reads a dense 32-channel tensor as (H, W/2, 64)");
   const int ck = (a.cin_pad % 64 == 0) ? 64 : ((a.cin_pad % 32 == 0) ? 32 : 16);
   ConvTcPlan* pl = new ConvTcPlan();
   ConvTcParams& p = pl->p;
   pl->ck = ck; pl->act_dtype = act_dtype;
   p.patch_mode = (a.k == 3 && a.stride == 1) ? 1 : 0;
   p.patch1 = (p.patch_mode && ck == 64 && p1_enabled()) ? 1 : 0;
-  const cuuint32_t box_rows = p.patch_mode ? TILE_Y + 2 : TILE_Y;
-  const cuuint32_t box_cols = p.patch1 ? P1_PITCH : TILE_X;
+  p.s2x = a.s2x ? 1 : 0;
+  const cuuint32_t box_rows = p.s2x ? TILE_Y + 1 : (p.patch_mode ? TILE_Y + 2 : TILE_Y);
+  const cuuint32_t box_cols = (p.patch1 || p.s2x) ? P1_PITCH : TILE_X;
   const cuuint64_t esz = 2;
   const cuuint64_t dim0 = (cuuint64_t)(a.cin_pad < a.in.pix_stride ? a.cin_pad : a.in.pix_stride);
   int rc = ACR_B200_OK;
-  if (a.stride == 1) {
+  if (a.s2x) {   // two row-parity views of the x-paired input (H, W/2, 64): rows 2r + py
+    for (int v = 0; v < 2 && !rc; ++v) {
+      const char* ptr = static_cast<const char*>(a.in.ptr) + (size_t)v * a.in.W * a.in.pix_stride * esz;
+      cuuint64_t dims[4] = {dim0, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H / 2, (cuuint64_t)a.batch};
+      cuuint64_t str[3] = {(cuuint64_t)a.in.pix_stride * esz, (cuuint64_t)2 * a.in.W * a.in.pix_stride * esz,
+                           (cuuint64_t)a.in.H * a.in.W * a.in.pix_stride * esz};
+      cuuint32_t box[4] = {(cuuint32_t)ck, box_cols, box_rows, 1};
+      rc = encode(&p.tmA[v], act_dtype, 4, ptr, dims, str, box, ck);
+    }
+    for (int v = 2; v < 4 && !rc; ++v) p.tmA[v] = p.tmA[0];
+  } else if (a.stride == 1) {
     cuuint64_t dims[4] = {dim0, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.batch};
     cuuint64_t str[3] = {(cuuint64_t)a.in.pix_stride * esz, (cuuint64_t)a.in.W * a.in.pix_stride * esz,
                          (cuuint64_t)a.in.H * a.in.W * a.in.pix_stride * esz};
@@ -868,7 +932,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
                      a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
                      (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) &&
-                     (epi_level >= 2 || (epi_level == 1 && (a.has_res || (a.k == 1 && a.cout_pad >= 256))));
+                     (epi_level >= 2 || (epi_level == 1 && (a.has_res || a.cout_pad == 64 || (a.cout_pad >= 256 && a.cin_pad <= 64))));
   // ring depth per epilogue warp: one buffer when a tile is one slab (the next tile's MMAs hide the residual fetch),
   // otherwise as many (<= 3) as fit next to the operand stages
   int epi_nb = 0;
@@ -931,7 +995,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.tma_out = want_tma_out ? 1 : 0;
   p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)(EPI_WARPS * p.epi_nb) * 4096u : 0u);
   const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
-  const int nA = p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks);
+  const int nA = p.s2x ? 2 : (p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks));
   // stages that must fit next to resident weights: a tile's worth of kx patches (3) for 3x3 stride-1 convs, 2 otherwise
   const size_t min_a = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * (size_t)p.a_stage_bytes;
   p.b_resident = (b_total + min_a + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
@@ -946,7 +1010,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   int SA = (int)(((size_t)SMEM_BUDGET - fixed - p.b_region_bytes) / p.a_stage_bytes);
   if (SA > 8) SA = 8;
   if (SA > 2 * nA && !p.patch1) SA = 2 * nA;  // no point in more stages than two super-tiles' worth of loads
-  if (p.patch1 && SA > 4) SA = 4;
+  if ((p.patch1 || p.s2x) && SA > 4) SA = 4;
   if (SA < 2) { set_error("conv_tc: shared memory plan does not fit (cout_pad %d, ck %d)", a.cout_pad, ck); delete pl; return ACR_B200_EINVAL; }
   p.SA = SA;
   pl->smem = fixed + p.b_region_bytes + (size_t)SA * p.a_stage_bytes;
@@ -978,6 +1042,10 @@ static int launch_inst(const ConvTcPlan* pl, cudaStream_t st) {
 template <int CK, typename T>
 static int launch_mode(const ConvTcPlan* pl, cudaStream_t st) {
   const int mode = (pl->p.patch_mode ? MODE_PATCH : 0) | (pl->p.b_resident ? MODE_RESIDENT : 0);
+  if (CK == 64 && pl->p.s2x) {
+    if (pl->p.debug) { set_error("conv_tc: no diagnostic instance of the x-paired stride-2 form"); return ACR_B200_EINVAL; }
+    return pl->p.b_resident ? launch_inst<64, T, MODE_RESIDENT | MODE_S2X>(pl, st) : launch_inst<64, T, MODE_S2X>(pl, st);
+  }
   if (CK == 64 && pl->p.patch1) {
     if (pl->p.debug) { set_error("conv_tc: diagnostic instances exist for the three-box form only (ACR_B200_P1=0)"); return ACR_B200_EINVAL; }
     if (pl->p.xpair) {

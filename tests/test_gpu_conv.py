@@ -132,3 +132,46 @@ def test_conv_tc_x_paired_32ch(flags):
         + (sd["b.bias"] - sd["b.running_mean"] * sc).view(1, -1, 1, 1) + res.float()
     exp = torch.relu(exp)
     assert (got - exp).abs().max().item() <= exp.abs().max().item() * 2 ** -6   # weights are rounded to bf16 here
+
+
+@pytest.mark.parametrize("cout,H", [(32, 64), (64, 64), (128, 32), (256, 32)])
+def test_conv_tc_stride2_x_paired_input(cout, H):
+    """3x3 stride-2 convs of DENSE 32-channel tensors (fuse-layer / transition convs of branch 0) read the input as
+    x-pairs (H, W/2, 64): two row-parity boxes per tile, taps = unaligned descriptor starts + K halves (MODE_S2X).
+    Packed through Engine._pack_conv(s2x=True); expected from the ORIGINAL weights with a plain fp32 stride-2 conv."""
+    import ctypes as C
+    import torch.nn.functional as Fn
+    from acr_b200.engine import Engine, _Blob
+    from tests.helpers import ctensor, rup
+    g = torch.Generator().manual_seed(cout + H)
+    B, W = 2, H
+    x = torch.randn(B, 32, H, W, generator=g).bfloat16()
+    sd = {"c.weight": torch.randn(cout, 32, 3, 3, generator=g) * (2 / 288) ** 0.5,
+          "b.weight": torch.rand(cout, generator=g) + 0.5, "b.bias": torch.randn(cout, generator=g) * 0.1,
+          "b.running_mean": torch.randn(cout, generator=g) * 0.1, "b.running_var": torch.rand(cout, generator=g) + 0.5}
+    eng = Engine(None, B, "cpu", dry_run=True)
+    blob = _Blob()
+    w_off, b_off = eng._pack_conv({k: v.numpy() for k, v in sd.items()}, blob, "c", "b", False, 64, cout, s2x=True)
+    xin = x.permute(0, 2, 3, 1).contiguous()                      # NHWC, C = 32 dense
+    nbytes = xin.numel() * 2
+    obytes = B * (H // 2) * (W // 2) * cout * 2
+    off_o = rup(nbytes, 1024)
+    arena = torch.zeros(off_o + rup(obytes, 1024), dtype=torch.uint8)
+    arena[:nbytes] = xin.view(torch.uint8).flatten()
+    op = L.Op()
+    op.kind, op.n_in = L.OP_CONV, 1
+    op.in_[0] = ctensor(0, 64, H, W // 2, 64, L.DT_BF16)           # the x-paired view of the input
+    op.out = ctensor(off_o, cout, H // 2, W // 2, cout, L.DT_BF16)
+    op.w_offset[0], op.w_offset[1] = w_off, b_off
+    op.k, op.stride, op.relu, op.has_residual, op.cin_pad, op.cout_pad = 3, 2, 1, 0, 64, cout
+    op.shift[0] = 8                                               # ACR_CONV_S2X
+    d_arena = arena.cuda()
+    d_blob = torch.frombuffer(bytearray(blob.tobytes()), dtype=torch.uint8).cuda()
+    L.check(L.load().acr_b200_run_op(C.byref(op), B, d_arena.data_ptr(), d_blob.data_ptr(), None, L.DT_BF16,
+                                     torch.cuda.current_stream().cuda_stream), "run_op")
+    torch.cuda.synchronize()
+    got = d_arena[off_o: off_o + obytes].cpu().view(torch.bfloat16).view(B, H // 2, W // 2, cout).permute(0, 3, 1, 2).float()
+    sc = sd["b.weight"] / torch.sqrt(sd["b.running_var"] + 1e-5)
+    exp = Fn.conv2d(x.float(), sd["c.weight"], None, 2, 1) * sc.view(1, -1, 1, 1) + (sd["b.bias"] - sd["b.running_mean"] * sc).view(1, -1, 1, 1)
+    exp = torch.relu(exp)
+    assert (got - exp).abs().max().item() <= exp.abs().max().item() * 2 ** -6   # weights are rounded to bf16 here

@@ -91,7 +91,7 @@ def test_network_forward(golden_dir):
     sd = synth_state_dict(0, bn_stats=load_bn_calibration(0))
     gi = torch.Generator().manual_seed(123)
     img = torch.randint(0, 256, (2, 512, 512, 3), generator=gi, dtype=torch.uint8)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(32, os.cpu_count()))   # > 64 threads oversubscribe these small convs (measured 40x slower at 128)
     out = net_ref.net_forward(sd, img, return_backbone=True)
     x = out["backbone"]
     assert abs(x.mean().item() - float(g["backbone_mean"])) < 1e-4

@@ -24,7 +24,11 @@ for spec in sys.argv[1:]:
     flags = fields[7] if len(fields) > 7 else 0
     cin_pad, cout_pad = rup(cin, 16), rup(cout, 16)
     Ho, Wo = H // s, W // s
-    in_bytes = B * H * W * cin_pad * 2
+    s2x = bool(flags & 8)       # ACR_CONV_S2X: "32,cout,3,2,H,0,W,8" = dense 32-channel input read as x-pairs (H, W/2, 64)
+    if s2x:
+        assert cin == 32 and s == 2 and k == 3
+        cin_pad = 64
+    in_bytes = B * H * W * (32 if s2x else cin_pad) * 2
     out_bytes = B * Ho * Wo * cout_pad * 2
     off_r = rup(in_bytes, 1024)
     off_o = rup(off_r + out_bytes, 1024)
@@ -36,7 +40,7 @@ for spec in sys.argv[1:]:
     op = L.Op()
     op.kind = L.OP_CONV
     op.n_in = 2 if res else 1
-    op.in_[0] = ctensor(0, cin, H, W, cin_pad, L.DT_BF16)
+    op.in_[0] = ctensor(0, 64, H, W // 2, 64, L.DT_BF16) if s2x else ctensor(0, cin, H, W, cin_pad, L.DT_BF16)
     op.in_[1] = ctensor(off_r, cout, Ho, Wo, cout_pad, L.DT_BF16)
     op.out = ctensor(off_o, cout, Ho, Wo, cout_pad, L.DT_BF16)
     op.shift[0] = flags
