@@ -199,6 +199,9 @@ struct ConvTcParams {
   const void* res;
   void* out;
   int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
+  int nsplit, nsub;   // N split: every super-tile is computed as nsplit "virtual tiles" of nsub = npad / nsplit output channels
+                      // (N = 256 would need all 512 TMEM columns for ONE tile: with two halves of 128 the accumulators are
+                      // double buffered again and the epilogue of one half overlaps the MMAs of the other; also lifts N > 256)
   int xpair;    // x-paired 32->32 conv run as 64->64 (see below): side taps are quarter blocks
   uint32_t idesc_half;
   int debug;    // MODE_DIAG bits (0 in the product path)
@@ -329,7 +332,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       pdl_wait();   // weights are constants; the activations below are the previous kernel's output
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int vt = blockIdx.x; vt < P.total_tiles * P.nsplit; vt += gridDim.x) {
+        const int tile = vt / P.nsplit, n_off = (vt - tile * P.nsplit) * P.nsub;
         const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
         const int y0 = (rem / P.tiles_x) * TILE_Y, x0 = (rem % P.tiles_x) * TILE_X;
         for (int a = 0; a < nA; ++a) {
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               mbar_wait(emptyB(sb), phb ^ 1u);
               if (elect_one_sync()) {
                 mbar_expect_tx(fullB(sb), P.b_block_bytes);
-                tma_load_2d(b_base + (uint32_t)sb * P.b_block_bytes, &P.tmB, fullB(sb), tap * P.cin_pad + cc * CK, 0);
+                tma_load_2d(b_base + (uint32_t)sb * P.b_block_bytes, &P.tmB, fullB(sb), tap * P.cin_pad + cc * CK, n_off);
               }
               __syncwarp();
               if (++sb == SB) { sb = 0; phb ^= 1u; }
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t b_block16 = P.b_block_bytes >> 4, a_stage16 = P.a_stage_bytes >> 4;
       // the right half's rows start one swizzle atom (8 pixels) into every image row of the box
       const uint32_t a_lo_base = (((a_base >> 4) & 0x3FFF) | lo_flags) + (uint32_t)h0 * (Cfg::kAtom >> 4);
-      const uint32_t b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;
+      const uint32_t b_lo_base = ((b_base >> 4) & 0x3FFF) | lo_flags;   // (shadowed per virtual tile below)
       const int cchunks = P.cchunks, ksteps = P.ksteps, taps = P.taps;
       const bool full_k = ksteps == CK / 16;
       int sa = 0, sb = 0;
@@ -441,13 +445,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       };
       auto issue = [&](uint32_t d0, uint32_t a_tap, uint32_t b_lo, uint32_t first, int kx) { issue_hi(d0, a_tap, hi_a, b_lo, first, kx); };
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b_lo_base0 = b_lo_base;
+      for (int vt = blockIdx.x; vt < P.total_tiles * P.nsplit; vt += gridDim.x, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;   // how often this buffer was used before
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) mbar_wait(tmem_empty(buf, h0 + hh), (use & 1u) ^ 1u);  // epilogue drained the accumulator(s)
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 + h0) * acc_stride;
+        // resident weights hold all N rows: this virtual tile multiplies rows [n_off, n_off + nsub)
+        const uint32_t b_lo_base = b_lo_base0 + (RESIDENT ? (uint32_t)((vt % P.nsplit) * P.nsub) * (Cfg::kRowBytes >> 4) : 0u);
         if (S2X) {
           // two A stages per tile (even-row box, odd-row box); tap (ky,kx): row offset (ky == 2), pair-column offset
           // (kx != 0), K half (kx != 1) -> k-steps {0,1} or {2,3} of the 64-wide row, same k-steps of the weight block
@@ -578,40 +585,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       //   * the finished slab leaves with one TMA store.
       // Synchronisation is per warp only: __syncwarp + proxy fences, bulk-group waits, no CTA-wide barrier.
       const int wi = warp - EPI_WARP0;
-      const int NB = P.epi_nb, G = P.npad >> 6;
+      const int NB = P.epi_nb, G = P.nsub >> 6;
       const uint32_t my_stage = stage_base + (uint32_t)(wi * NB) * 4096u;
       const uint32_t sw = (uint32_t)(lane & 7);
       const bool has_res = P.has_res != 0;
-      const int my_tiles = ((int)blockIdx.x < P.total_tiles) ? (P.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int vtiles = P.total_tiles * P.nsplit;
+      const int my_tiles = ((int)blockIdx.x < vtiles) ? (vtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
       const int total_slabs = my_tiles * G;
-      auto slab_xy = [&](int k, int& n, int& tx, int& ty, int& c0) {
-        const int tile = (int)blockIdx.x + (k / G) * (int)gridDim.x;
-        c0 = (k % G) * 64;
+      // slab k -> image n, pixel origin (tx, ty), tensor channel cg (for TMA) -- cg includes the virtual tile's N offset
+      auto slab_xy = [&](int k, int& n, int& tx, int& ty, int& cg) {
+        const int vt = (int)blockIdx.x + (k / G) * (int)gridDim.x;
+        const int tile = vt / P.nsplit;
+        cg = (vt - tile * P.nsplit) * P.nsub + (k % G) * 64;
         n = tile / P.tiles_per_img;
         const int rem = tile % P.tiles_per_img;
         ty = (rem / P.tiles_x) * TILE_Y + 4 * q;
         tx = (rem % P.tiles_x) * TILE_X + h * HALF_X;
       };
       auto load_res = [&](int k) {    // lane 0 only
-        int n, tx, ty, c0;
-        slab_xy(k, n, tx, ty, c0);
+        int n, tx, ty, cg;
+        slab_xy(k, n, tx, ty, cg);
         const int b = k % NB;
         mbar_expect_tx(res_full(wi * 3 + b), 4096u);
-        tma_load_4d(my_stage + (uint32_t)b * 4096u, &P.tmRes, res_full(wi * 3 + b), c0, tx, ty, n);
+        tma_load_4d(my_stage + (uint32_t)b * 4096u, &P.tmRes, res_full(wi * 3 + b), cg, tx, ty, n);
       };
       const int ahead = NB > 1 ? NB - 1 : 1;     // residual loads in flight beyond the slab being processed
       if (has_res && lane == 0)
         for (int k = 0; k < ahead && k < total_slabs; ++k) load_res(k);
       int k = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      for (int vt = blockIdx.x; vt < vtiles; vt += gridDim.x, ++it) {
         const int buf = nbuf == 2 ? (it & 1) : 0;
         const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
         mbar_wait(tmem_full(buf, h), use & 1u);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
         for (int g = 0; g < G; ++g, ++k) {
-          int n, tx, ty, c0;
-          slab_xy(k, n, tx, ty, c0);
+          int n, tx, ty, cg;
+          slab_xy(k, n, tx, ty, cg);
+          const int c0 = g * 64;                                 // column inside the accumulator
           const int b = k % NB;
           const uint32_t row = my_stage + (uint32_t)b * 4096u + (uint32_t)lane * 128u;
           uint32_t v[4][16];
@@ -636,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             float f[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + c * 16 + 4 * i);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cg + c * 16 + 4 * i);
               f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
               f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
             }
@@ -658,7 +669,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA unit
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&P.tmOut, my_stage + (uint32_t)b * 4096u, c0, tx, ty, n);
+            tma_store_4d(&P.tmOut, my_stage + (uint32_t)b * 4096u, cg, tx, ty, n);
             bulk_commit();
             const int kn = k + ahead;                            // next residual to fetch
             if (has_res && kn < total_slabs) {
@@ -673,21 +684,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (lane == 0) bulk_wait_all();                            // staging must outlive the stores
     } else
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int vt = blockIdx.x; vt < P.total_tiles * P.nsplit; vt += gridDim.x, ++it) {
       const int buf = nbuf == 2 ? (it & 1) : 0;
       const uint32_t use = nbuf == 2 ? ((uint32_t)it >> 1) : (uint32_t)it;
+      const int tile = vt / P.nsplit, n_off = (vt - tile * P.nsplit) * P.nsub;   // output channels [n_off, n_off + nsub)
       const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
       const int oy = (rem / P.tiles_x) * TILE_Y + (r >> 3), ox = (rem % P.tiles_x) * TILE_X + h * HALF_X + (r & 7);
       const size_t pix = ((size_t)n * P.Ho + oy) * P.Wo + ox;
       const int ty0 = (rem / P.tiles_x) * TILE_Y, tx0 = (rem % P.tiles_x) * TILE_X + h * HALF_X;
-      const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride : nullptr;
+      const T* resp = P.has_res ? reinterpret_cast<const T*>(P.res) + pix * P.res_stride + n_off : nullptr;
       // bias: per CTA from shared memory, or (folded part-head conv) one row per image from global
-      const float* bsrc = P.bias_per_image ? P.bias + (size_t)n * P.npad : s_bias;
+      const float* bsrc = P.bias_per_image ? P.bias + (size_t)n * P.npad : s_bias + n_off;
       uint4 rr[4][2];
       if (resp) {   // prefetch the first 64 residual channels while the MMAs are still running
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c * 16 < P.npad) {
+          if (c * 16 < P.nsub) {
             if (P.vec256) ldg256(resp + c * 16, rr[c][0], rr[c][1]);
             else {
               rr[c][0] = *reinterpret_cast<const uint4*>(resp + c * 16);
@@ -704,14 +716,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         continue;
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * P.acc_stride);
-      for (int g0 = 0; g0 < P.npad; g0 += 64) {
-        const int nch = min(4, (P.npad - g0) >> 4);  // 16-column chunks in this group (warp-uniform)
+      for (int g0 = 0; g0 < P.nsub; g0 += 64) {
+        const int nch = min(4, (P.nsub - g0) >> 4);  // 16-column chunks in this group (warp-uniform)
         uint32_t v[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < nch) tmem_ld16(t_row + (uint32_t)(g0 + c * 16), v[c]);
         tmem_ld_wait();
-        if (g0 + 64 >= P.npad) {  // all TMEM reads of this tile done: hand the accumulator back
+        if (g0 + 64 >= P.nsub) {  // all TMEM reads of this tile done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(buf, h));
@@ -729,11 +741,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b4 = P.bias_per_image ? *reinterpret_cast<const float4*>(bsrc + c0 + 4 * i)
-                                               : *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);   // LDS, not a generic load
+                                               : *reinterpret_cast<const float4*>(s_bias + n_off + c0 + 4 * i);   // LDS, not a generic load
             f[4 * i + 0] = __uint_as_float(v[c][4 * i + 0]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
             f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
           }
-          if (P.pow11_ch0 && c0 == 0) f[0] = powf(1.1f, f[0]);   // cam scale channel (acr/model.py:95-96)
+          if (P.pow11_ch0 && c0 + n_off == 0) f[0] = powf(1.1f, f[0]);   // cam scale channel (acr/model.py:95-96)
           if (resp) {
             float x[16];
             unpack8<T>(rr[c][0], x);
@@ -742,7 +754,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) f[i] += x[i];
             // this chunk's residual registers are free again: fetch the same chunk of the NEXT 64-channel group now,
             // so that its DRAM round trip overlaps the rest of this group (wide layers are HBM bound)
-            if (c0 + 64 < P.npad) {
+            if (c0 + 64 < P.nsub) {
               if (P.vec256) ldg256(resp + c0 + 64, rr[c][0], rr[c][1]);
               else {
                 rr[c][0] = *reinterpret_cast<const uint4*>(resp + c0 + 64);
@@ -755,11 +767,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
           }
           if (P.out_f32) {
-            float* o = reinterpret_cast<float*>(P.out) + pix * P.out_stride + c0;
+            float* o = reinterpret_cast<float*>(P.out) + pix * P.out_stride + n_off + c0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
-            T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + c0;
+            T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride + n_off + c0;
             if (tma_out) {
               sts128(stage_row + ((((uint32_t)(2 * c)) ^ stage_sw) << 4), pack8<T>(f));
               sts128(stage_row + ((((uint32_t)(2 * c + 1)) ^ stage_sw) << 4), pack8<T>(f + 8));
@@ -774,7 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           fence_proxy_async_smem();
           named_bar_sync(1 + h, 128);
           if (r == 0) {
-            tma_store_4d(&P.tmOut, stage_base + (uint32_t)h * 16384u, g0, tx0, ty0, n);
+            tma_store_4d(&P.tmOut, stage_base + (uint32_t)h * 16384u, n_off + g0, tx0, ty0, n);
             bulk_commit();
           }
         }
@@ -850,6 +862,13 @@ static bool p1_enabled() {
   return !(e && atoi(e) == 0);
 }
 
+// ACR_B200_NSPLIT=0 (read at plan creation) computes N = 256 layers as one 256-column accumulator per half tile again
+// (single-buffered TMEM): A/B timing of the two-halves form.
+static bool nsplit_enabled() {
+  const char* e = getenv("ACR_B200_NSPLIT");
+  return !(e && atoi(e) == 0);
+}
+
 // ACR_B200_EPI (read at plan creation): 0 = direct-store epilogue everywhere, 1 (default) = staged epilogue where it
 // measured faster (profiles/r2_conv_ab_epilogue.log, r2_conv_ab_singlebox.log): every layer with a residual -- its
 // DRAM latency leaves the critical path: 64->256 1x1 + residual 1123 -> 730 us = the HBM copy rate --, every N = 64
@@ -862,7 +881,7 @@ static int epi_staged_level() {
 
 int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   ACR_CHECK_ARG(a.out.H % TILE_Y == 0 && a.out.W % TILE_X == 0, "conv_tc: output %dx%d is not a multiple of the 16x16 super-tile", a.out.H, a.out.W);
-  ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 256,
+  ACR_CHECK_ARG(a.in.pix_stride % 8 == 0 && a.cin_pad % 16 == 0 && a.cout_pad % 16 == 0 && a.cout_pad <= 1024,
                 "conv_tc: channel alignment");
   ACR_CHECK_ARG(a.in.dtype == act_dtype, "conv_tc: input dtype mismatch");
   ACR_CHECK_ARG(!(a.k == 1 && a.stride != 1), "conv_tc: 1x1 stride-2 unsupported");
@@ -911,14 +930,18 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
       rc = encode(&p.tmA[v], act_dtype, 4, ptr, dims, str, box, ck);
     }
   }
-  if (!rc) {
-    const int taps = a.k * a.k;
-    cuuint64_t dims[2] = {(cuuint64_t)taps * a.cin_pad, (cuuint64_t)a.cout_pad};
-    cuuint64_t str[1] = {(cuuint64_t)taps * a.cin_pad * esz};
-    cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)a.cout_pad};
-    rc = encode(&p.tmB, act_dtype, 2, a.w, dims, str, box, ck);
+  // N split (see ConvTcParams::nsplit): mandatory above 256 output channels (one UMMA instruction / the TMEM columns),
+  // chosen at 256 so that the accumulators are double buffered again (ACR_B200_NSPLIT=0 keeps N = 256 whole)
+  int nsplit = 1;
+  if (a.cout_pad > 256) {
+    nsplit = (a.cout_pad + 255) / 256;
+    while (a.cout_pad % nsplit || (a.cout_pad / nsplit) % 16) ++nsplit;
+  } else if (a.cout_pad == 256 && !a.bias_per_image && !a.pow11_ch0 && nsplit_enabled()) {
+    nsplit = 2;
   }
-  const bool want_tma_out = a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
+  const int nsub = a.cout_pad / nsplit;
+  ACR_CHECK_ARG(nsub <= 256 && nsub % 16 == 0 && (nsplit == 1 || !a.bias_per_image), "conv_tc: cannot split N = %d", a.cout_pad);
+  const bool want_tma_out = a.out.dtype != ACR_DT_F32 && nsub % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
                             a.out.pix_stride % 8 == 0 && !tma_out_disabled();
   if (!rc && want_tma_out) {
     cuuint64_t dims[4] = {(cuuint64_t)a.cout_pad, (cuuint64_t)a.out.W, (cuuint64_t)a.out.H, (cuuint64_t)a.batch};
@@ -929,7 +952,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   }
   // staged epilogue (per-warp TMA store + TMA residual prefetch): N = 64, 16-bit output, shared bias
   const int epi_level = epi_staged_level();
-  bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && a.cout_pad % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
+  bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && nsub % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
                      a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
                      (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) &&
                      (epi_level >= 2 || (epi_level == 1 && (a.has_res || a.cout_pad == 64 || (a.cout_pad >= 256 && a.cin_pad <= 64))));
@@ -937,10 +960,10 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   // otherwise as many (<= 3) as fit next to the operand stages
   int epi_nb = 0;
   if (want_staged) {
-    const size_t a_st = (size_t)(box_rows * box_cols) * ck * 2, b_blk = (size_t)a.cout_pad * ck * 2;
-    const size_t b_tot = (size_t)a.k * a.k * (a.cin_pad / ck) * b_blk;
+    const size_t a_st = (size_t)(box_rows * box_cols) * ck * 2, b_blk = (size_t)nsub * ck * 2;
+    const size_t b_tot = a.cout_pad <= 256 ? (size_t)a.k * a.k * (a.cin_pad / ck) * a.cout_pad * ck * 2 : (size_t)1 << 40;
     const size_t min_a0 = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * a_st;
-    for (int nb = (a.cout_pad == 64 ? 1 : 3); nb >= 1 && !epi_nb; --nb) {
+    for (int nb = (nsub == 64 ? 1 : 3); nb >= 1 && !epi_nb; --nb) {
       const size_t fx = 1024 + 1024 + 512 + (size_t)EPI_WARPS * nb * 4096;
       if (b_tot + min_a0 + fx <= (size_t)SMEM_BUDGET || 4 * b_blk + min_a0 + fx <= (size_t)SMEM_BUDGET) epi_nb = nb;
     }
@@ -970,7 +993,8 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   p.vec256 = (a.out.dtype != ACR_DT_F32) && ((uintptr_t)a.out.ptr % 32 == 0) && (a.out.pix_stride % 16 == 0) &&
              (!a.has_res || (((uintptr_t)a.res.ptr % 32 == 0) && (a.res.pix_stride % 16 == 0)));
   if (p.cchunks == 1 && (int)((dim0 + 15) / 16) < p.ksteps) p.ksteps = (int)((dim0 + 15) / 16);
-  p.npad = a.cout_pad; p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
+  p.npad = a.cout_pad; p.nsplit = nsplit; p.nsub = nsub;
+  p.relu = a.relu; p.has_res = a.has_res; p.out_f32 = a.out.dtype == ACR_DT_F32;
   p.bias_per_image = a.bias_per_image; p.pow11_ch0 = a.pow11_ch0;
   p.xpair = a.xpair;
   { const char* e = getenv("ACR_B200_CONV_DIAG"); p.debug = e ? atoi(e) : 0; }
@@ -981,17 +1005,17 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   // per super-tile two accumulators (left/right half) of acc_stride columns (power of two >= cout_pad);
   // double buffered when 4 of them fit the 512 TMEM columns
   p.acc_stride = 16;
-  while (p.acc_stride < a.cout_pad) p.acc_stride *= 2;
+  while (p.acc_stride < nsub) p.acc_stride *= 2;
   p.nbuf = (4 * p.acc_stride <= 512) ? 2 : 1;
   p.tmem_cols = p.nbuf * 2 * p.acc_stride < 32 ? 32 : p.nbuf * 2 * p.acc_stride;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B = bf16|f16, K-major both, N, M=128
   const uint32_t fmt = act_dtype == ACR_DT_BF16 ? 1u : 0u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.cout_pad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nsub >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.idesc_half = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   // shared-memory plan
   p.a_stage_bytes = (uint32_t)(box_rows * box_cols) * ck * 2;
-  p.b_block_bytes = (uint32_t)a.cout_pad * ck * 2;
-  const size_t b_total = (size_t)p.taps * p.cchunks * p.b_block_bytes;
+  // resident weights: every output channel of a (tap, chunk) in one box (<= 256 rows); streamed: one virtual tile's rows
+  const size_t b_total = a.cout_pad <= 256 ? (size_t)p.taps * p.cchunks * a.cout_pad * ck * 2 : (size_t)1 << 40;
   p.tma_out = want_tma_out ? 1 : 0;
   p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)(EPI_WARPS * p.epi_nb) * 4096u : 0u);
   const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
@@ -999,6 +1023,15 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   // stages that must fit next to resident weights: a tile's worth of kx patches (3) for 3x3 stride-1 convs, 2 otherwise
   const size_t min_a = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * (size_t)p.a_stage_bytes;
   p.b_resident = (b_total + min_a + fixed <= (size_t)SMEM_BUDGET) ? 1 : 0;
+  p.b_block_bytes = (uint32_t)(p.b_resident ? a.cout_pad : nsub) * ck * 2;
+  {
+    const int taps = a.k * a.k;
+    cuuint64_t dims[2] = {(cuuint64_t)taps * a.cin_pad, (cuuint64_t)a.cout_pad};
+    cuuint64_t str[1] = {(cuuint64_t)taps * a.cin_pad * esz};
+    cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)(p.b_resident ? a.cout_pad : nsub)};
+    rc = encode(&p.tmB, act_dtype, 2, a.w, dims, str, box, ck);
+    if (rc) { delete pl; return rc; }
+  }
   if (p.b_resident) {
     p.b_region_bytes = (uint32_t)((b_total + 1023) & ~(size_t)1023);
     p.SB = 0;
@@ -1014,7 +1047,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   if (SA < 2) { set_error("conv_tc: shared memory plan does not fit (cout_pad %d, ck %d)", a.cout_pad, ck); delete pl; return ACR_B200_EINVAL; }
   p.SA = SA;
   pl->smem = fixed + p.b_region_bytes + (size_t)SA * p.a_stage_bytes;
-  pl->grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  pl->grid = p.total_tiles * nsplit < num_sms() ? p.total_tiles * nsplit : num_sms();
   *out = pl;
   return ACR_B200_OK;
 }

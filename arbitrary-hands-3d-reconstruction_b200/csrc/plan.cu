@@ -45,7 +45,7 @@ static int make_conv_args(const acr_b200_op& op, int batch, char* arena, const c
   ACR_CHECK_ARG((op.k == 1 || op.k == 3) && (op.stride == 1 || op.stride == 2), "conv: k/stride unsupported");
   if (a->s2x) ACR_CHECK_ARG(op.stride == 2 && a->out.H * 2 == a->in.H && a->out.W == a->in.W, "conv: x-paired stride-2 spatial mismatch");
   else ACR_CHECK_ARG(a->out.H * op.stride == a->in.H && a->out.W * op.stride == a->in.W, "conv: spatial mismatch");
-  ACR_CHECK_ARG(op.cout_pad % 16 == 0 && op.cin_pad % 16 == 0 && op.cout_pad <= 256, "conv: padded channel counts");
+  ACR_CHECK_ARG(op.cout_pad % 16 == 0 && op.cin_pad % 16 == 0 && op.cout_pad <= 1024, "conv: padded channel counts");
   ACR_CHECK_ARG(a->out.pix_stride >= op.cout_pad, "conv: output buffer narrower than cout_pad");
   return ACR_B200_OK;
 }
