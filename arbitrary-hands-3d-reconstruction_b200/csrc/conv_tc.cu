@@ -936,7 +936,10 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   if (a.cout_pad > 256) {
     nsplit = (a.cout_pad + 255) / 256;
     while (a.cout_pad % nsplit || (a.cout_pad / nsplit) % 16) ++nsplit;
-  } else if (a.cout_pad == 256 && !a.bias_per_image && !a.pow11_ch0 && nsplit_enabled()) {
+  } else if (a.cout_pad == 256 && a.cin_pad >= 256 && a.k == 3 && !a.bias_per_image && !a.pow11_ch0 && nsplit_enabled()) {
+    // measured (profiles/r2_conv_ab_nsplit.log): the MMA-bound 256->256 3x3 layers gain 8-18 % from the double-buffered
+    // halves; layers whose weights stream per tile with a short K (34->256, 64->256) lose (each half re-loads A and
+    // issues twice the TMA boxes per unit of math), so they keep N = 256 whole
     nsplit = 2;
   }
   const int nsub = a.cout_pad / nsplit;
