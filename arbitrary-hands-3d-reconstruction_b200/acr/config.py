@@ -17,6 +17,8 @@ _DEFAULTS = dict(
     tab="ACR_hrnet_internet", backbone="hrnet",          # config.py:95 (flag is only a log tag)
     model_precision="bf16",                               # reference: fp32|fp16 (config.py:96); here bf16|fp16 = tensor-core
                                                           # plans, fp32 = the (slow, reference-accurate) validation plan
+    hrnet_width=32,                                        # 32 = the reference's HRNet-W32 (the only trunk it contains); 48 = the
+                                                          # HRNet-W48 trunk of BASELINE configs[4] (no reference: parity unpinned)
     input_size=512,                                        # config.py:61
     centermap_size=64, centermap_conf_thresh=0.35,         # config.py:130-131
     kernel_sizes=[5], max_hand=4,                          # config.py:185,161

@@ -15,7 +15,7 @@ import torch.nn as nn
 from acr.config import args
 from acr.result_parser import ResultParser
 from acr_b200.engine import Engine
-from acr_b200.netspec import build_acr_spec
+from acr_b200.netspec import WIDTHS, WIDTHS_W48, build_acr_spec
 
 BN_MOMENTUM = 0.1
 _MAP_KEYS = ('l_params_maps', 'r_params_maps', 'l_center_map', 'r_center_map', 'l_prior_maps', 'r_prior_maps', 'segms')
@@ -81,7 +81,8 @@ class LazyOutputs(dict):
 class ACR(nn.Module):
     def __init__(self, **kwargs):
         super().__init__()
-        self._spec = build_acr_spec(args().input_size)
+        self._widths = {32: WIDTHS, 48: WIDTHS_W48}[int(getattr(args(), 'hrnet_width', 32))]
+        self._spec = build_acr_spec(args().input_size, widths=self._widths)
         g = torch.Generator().manual_seed(0)
         for key, (shape, kind) in self._spec.params.items():
             if kind == 'bn_nbt':
@@ -145,7 +146,7 @@ class ACR(nn.Module):
             self._engines.move_to_end(key)
             return self._engines[key]
         eng = Engine(self.state_dict(), batch, dev, dt, args().input_size, debug_ref_conv=self.debug_ref_conv,
-                     head_only=head_only, weights=self._blobs.get(bkey))
+                     head_only=head_only, weights=self._blobs.get(bkey), widths=self._widths)
         self._blobs[bkey] = eng.weights
         self._engines[key] = eng
         while len(self._engines) > max(1, self.max_engines):

@@ -99,7 +99,7 @@ class Engine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, device, act_dtype=torch.bfloat16,
                  input_size: int = 512, debug_ref_conv: bool = False, reuse_memory: bool = True,
                  dry_run: bool = False, keep_extra=(), stem_on_tensor_cores: bool = True,
-                 head_only: bool = False, weights: Optional[torch.Tensor] = None):
+                 head_only: bool = False, weights: Optional[torch.Tensor] = None, widths=None):
         self.keep_extra = tuple(keep_extra)   # extra tensor names kept alive after the run (tests)
         self.dry_run = dry_run      # layout only (arena size, op list); used by CPU tests
         if not dry_run and not torch.cuda.is_available():
@@ -116,7 +116,9 @@ class Engine:
         self.npw = np.float32 if self.f32 else np.uint16      # numpy type of one packed weight
         self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
         self.head_only = head_only
-        self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0")
+        from .netspec import WIDTHS
+        self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0",
+                                            widths=tuple(widths) if widths else WIDTHS)
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)
         self.debug_ref_conv = debug_ref_conv or self.f32
@@ -326,7 +328,8 @@ class Engine:
                 # K per tap: 33/34-channel inputs are padded to ONE 64-channel chunk (TMA zero-fills the
                 # channels beyond the 48-wide buffer) instead of three 16-channel chunks: a TMA box costs
                 # ~620 clk whatever its size, so fewer, fatter boxes win (tools/tma_bench.cu)
-                o.cin_pad = 64 if 32 < x.C <= 64 else _rup(x.C, 16)
+                # (same rule for the wider trunks: 48 -> 64, 96 -> 128 with zero-filled tails)
+                o.cin_pad = _rup(x.C, 64) if x.C > 32 else _rup(x.C, 16)
                 o.cout_pad = _rup(r["out"].C, 16)
                 if "stem" in a:
                     # weights (64,3,3,3) OIHW -> (64, 32, 1, 1) with input channel (ky*3+kx)*3+ci; BN folded by pack_conv

@@ -147,8 +147,9 @@ def _bottleneck(g: NetSpec, x: Tensor, p: str, planes: int, down: bool) -> Tenso
 
 
 def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bool,
-               out0: Optional[Tensor] = None) -> List[Tensor]:
+               out0: Optional[Tensor] = None, WIDTHS: Tuple[int, ...] = None) -> List[Tensor]:
     # acr/model.py:571-686; 4 BasicBlocks per branch, then the fuse layers
+    WIDTHS = WIDTHS or globals()["WIDTHS"]
     nb = len(xs)
     xs = list(xs)
     for b in range(nb):
@@ -177,10 +178,21 @@ def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bo
     return outs
 
 
-def build_acr_spec(input_size: int = 512, merge_stems: bool = True) -> NetSpec:
+WIDTHS_W48 = (48, 96, 192, 384)
+
+
+def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tuple[int, ...] = WIDTHS) -> NetSpec:
     """Full ACR network for one image of ``input_size`` x ``input_size``.  ``merge_stems=False`` keeps the eight
-    head stem convs as eight launches (A/B timing of the merged form)."""
+    head stem convs as eight launches (A/B timing of the merged form).
+
+    ``widths``: branch widths of the HRNet trunk.  (32, 64, 128, 256) is the reference's network (the only one it
+    contains: /root/reference/acr/model.py:796-797).  WIDTHS_W48 = (48, 96, 192, 384) is the HRNet-W48
+    trunk BASELINE.json's configs[4] names: it has no reference implementation -- the same topology with wider
+    branches, the heads reading a (widths[0] + 2)-channel map -- so its PARITY IS UNPINNED (no golden can exist); it is
+    measured for throughput and pinned op by op only against the oracle's per-op restatement."""
     g = NetSpec()
+    g.widths = tuple(widths)
+    W0, W1, W2, W3 = g.widths
     S = input_size
     img = Tensor("image", 3, S, S, "u8")
     g.tensors[img.name] = img
@@ -197,32 +209,32 @@ def build_acr_spec(input_size: int = 512, merge_stems: bool = True) -> NetSpec:
         x = _bottleneck(g, x, f"backbone.layer1.{i}", 64, down=(i == 0))
 
     # ---- transition1 + stage2 (acr/model.py:796-805, 841-847)
-    xs = [g.conv(x, "backbone.transition1.0.0", "backbone.transition1.0.1", 32, 3, relu=True),
-          g.conv(x, "backbone.transition1.1.0.0", "backbone.transition1.1.0.1", 64, 3, s=2, relu=True)]
-    xs = _hr_module(g, "backbone.stage2.0", xs, True)
+    xs = [g.conv(x, "backbone.transition1.0.0", "backbone.transition1.0.1", W0, 3, relu=True),
+          g.conv(x, "backbone.transition1.1.0.0", "backbone.transition1.1.0.1", W1, 3, s=2, relu=True)]
+    xs = _hr_module(g, "backbone.stage2.0", xs, True, WIDTHS=g.widths)
 
     # ---- transition2 + stage3 (4 modules, 3 branches)
-    xs.append(g.conv(xs[-1], "backbone.transition2.2.0.0", "backbone.transition2.2.0.1", 128, 3, s=2, relu=True))
+    xs.append(g.conv(xs[-1], "backbone.transition2.2.0.0", "backbone.transition2.2.0.1", W2, 3, s=2, relu=True))
     for m in range(4):
-        xs = _hr_module(g, f"backbone.stage3.{m}", xs, True)
+        xs = _hr_module(g, f"backbone.stage3.{m}", xs, True, WIDTHS=g.widths)
 
     # ---- transition3 + stage4 (3 modules, 4 branches; last keeps only branch 0)
-    xs.append(g.conv(xs[-1], "backbone.transition3.3.0.0", "backbone.transition3.3.0.1", 256, 3, s=2, relu=True))
+    xs.append(g.conv(xs[-1], "backbone.transition3.3.0.0", "backbone.transition3.3.0.1", W3, 3, s=2, relu=True))
     # the backbone output lands in channels [0:32) of the 34-channel coord-concat buffer
     F = S // 4
-    xcat = g._t(34, F, F, "xcat")
-    feat = Tensor("feat32", 32, F, F, "act", base=xcat, c_off=0)
+    xcat = g._t(W0 + 2, F, F, "xcat")
+    feat = Tensor("feat32", W0, F, F, "act", base=xcat, c_off=0)   # ("feat32": the name, not the width)
     g.tensors[feat.name] = feat
     for m in range(3):
         last = m == 2
-        xs = _hr_module(g, f"backbone.stage4.{m}", xs, not last, out0=feat if last else None)
+        xs = _hr_module(g, f"backbone.stage4.{m}", xs, not last, out0=feat if last else None, WIDTHS=g.widths)
     x = xs[0]
     assert x is feat
     # coord channels 32,33 are constants written once (acr/model.py:52, 340-369)
     g.ops.append(Op("coordcat", xcat, [feat], {}))
 
     # ---- SegmNet (acr/model.py:374-463): bilinear x2, DoubleConv 32->16->64, conv 64->33+BN+ReLU, conv 33->33
-    up = g._t(32, 2 * F, 2 * F, "bilin")
+    up = g._t(W0, 2 * F, 2 * F, "bilin")
     g.ops.append(Op("bilinear2x", up, [feat], {}))
     pu = "backbone.hand_segm.segm_head.upsampler.up1.conv.double_conv"
     y = g.conv(up, pu + ".0", pu + ".1", 16, 3, relu=True, bias=True)
@@ -293,7 +305,7 @@ def build_acr_spec(input_size: int = 512, merge_stems: bool = True) -> NetSpec:
 
     # ---- dead-but-present parameters (acr/model.py:181, 262-286): kept so that
     #      state_dict() has the reference's 2067 keys; never executed.
-    g._reg("segmentation_layers.1.0.weight", (256, 34, 3, 3), "conv_w")
+    g._reg("segmentation_layers.1.0.weight", (256, W0 + 2, 3, 3), "conv_w")
     g._reg("segmentation_layers.1.0.bias", (256,), "conv_b")
     g._reg_bn("segmentation_layers.1.1", 256)
     g._reg("segmentation_layers.2.0.weight", (33, 256, 1, 1), "conv_w")

@@ -224,7 +224,13 @@ def run_b200(args):
     cfg_args().model_precision = args.dtype
     cfg_args().return_maps = False
     B = args.batch
-    sd = synth_state_dict(0, bn_stats=load_bn_calibration(0))
+    w48 = args.backbone == "hrnet_w48"
+    if w48:     # BASELINE configs[4]'s trunk: no reference implementation exists (parity unpinned), throughput only
+        from acr_b200.netspec import WIDTHS_W48, build_acr_spec
+        cfg_args().hrnet_width = 48
+        sd = synth_state_dict(0, spec=build_acr_spec(512, widths=WIDTHS_W48))
+    else:
+        sd = synth_state_dict(0, bn_stats=load_bn_calibration(0))
     assets = {"left": make_synthetic_mano("left"), "right": make_synthetic_mano("right")}
     app = ACR(state_dict=sd, mano_assets=assets)
     gi = torch.Generator().manual_seed(1000 + rank)            # every rank generates its own shard
@@ -405,7 +411,7 @@ def run_b200(args):
     n_hands = int(bufs.counts[2])
     if rank == 0:
         peaks = load_peaks()
-        traffic, alg_gb, traffic_note = load_traffic(B)
+        traffic, alg_gb, traffic_note = (None, None, "no ncu capture of the W48 plan") if w48 else load_traffic(B)
         # MANO vertices of the stand-alone launch above vs the oracle (numpy restatement pinned to the reference)
         from oracle import mano_ref as _mano_ref
         poses_, betas_, cam_, offs_, ht_, mo = mano_io
@@ -429,10 +435,12 @@ def run_b200(args):
         e2e_s = world * B * args.steps / (ms_e2e / 1e3)
         launches = eng.num_launches + 3 + 1 + (1 if cfg_args().cam_trans_mode == "lstsq" else 0)
         out = {
-            "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC.replace("W32", "W48") if w48 else METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"batch {B}/GPU, 512x512 uint8 RGB, HRNet-W32, two-hand MANO (BASELINE configs[2])",
+            "config": {"workload": (f"batch {B}/GPU, 512x512 uint8 RGB, HRNet-W48 trunk (restated: the reference ships only W32 -- PARITY "
+                                    "UNPINNED, throughput only), two-hand MANO (BASELINE configs[4] per GPU)") if w48 else
+                                   f"batch {B}/GPU, 512x512 uint8 RGB, HRNet-W32, two-hand MANO (BASELINE configs[2])",
                        "global_batch": B * world, "hands_per_step_rank0": n_hands,
                        "parallelism": f"frames sharded over {world} rank(s); {gather_mode}" if world > 1 else "single GPU",
                        "l2_hygiene": f"inputs {B * 786432 / 2**20:.0f} MiB + {eng.arena_bytes / 2**20:.0f} MiB activations per step >> 126 MB L2",
@@ -451,7 +459,7 @@ def run_b200(args):
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "algorithmic_gflop_per_launch_set": conv_gflop * B,
                          "conv_ms_per_step": conv_ms, "conv_share_of_plan": conv_ms / total_prof_ms if total_prof_ms else None,
-                         "whole_net_tflops": GFLOP_PER_IMAGE * B / (ms_value / args.steps)},
+                         "whole_net_tflops": eng.flops_per_image / 1e9 * B / (ms_value / args.steps)},
             "profile_ms_by_kind": {str(k): round(v[0], 3) for k, v in prof.items()},
             # BASELINE metric, second half + north-star MANO target (>= 0.60 of the HBM roofline): the kernel alone
             "mano_verts_max_abs_err": verts_err,
@@ -488,13 +496,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--backbone", default="hrnet_w32", choices=["hrnet_w32", "hrnet_w48"],
+                    help="hrnet_w48: the wider trunk of BASELINE configs[4]; no reference exists for it (parity unpinned)")
     ap.add_argument("--ref-batch", type=int, default=8, help="frames per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: vertex all-gather fused into the MANO kernel (symmetric memory) or a separate NCCL call")
     args = ap.parse_args()
-    if args.gpus > 1:
-        args.cpu_baseline = False
+    if args.gpus > 1 or args.backbone != "hrnet_w32":
+        args.cpu_baseline = False          # the CPU arm is the reference's own network (HRNet-W32)
     if args.impl == "reference":
         run_reference(args)
     else:

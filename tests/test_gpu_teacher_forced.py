@@ -77,8 +77,9 @@ def sweep(eng, sd, image, tol):
         elif kind == L.OP_COORD:
             xc = eng.view(r["out"]).float().cpu()
             exp = op_ref.coord(xc.shape[1], xc.shape[2])[None].expand(xc.shape[0], -1, -1, -1)
-            checks.append(("coord channels", xc[..., 32:34].permute(0, 3, 1, 2), exp))
-            assert float(xc[..., 34:].abs().max()) == 0.0, "pad channels of the coord concat are not zero"
+            w0 = eng.spec.widths[0]
+            checks.append(("coord channels", xc[..., w0:w0 + 2].permute(0, 3, 1, 2), exp))
+            assert float(xc[..., w0 + 2:].abs().max()) == 0.0, "pad channels of the coord concat are not zero"
         elif kind == L.OP_POOL:
             pool_in = r["ins"]                                                  # partials are checked after the merge
         elif kind == L.OP_PARTHEAD:
@@ -97,10 +98,10 @@ def sweep(eng, sd, image, tol):
     return rows
 
 
-def _run(sd, image, dtype):
+def _run(sd, image, dtype, widths=None):
     from acr_b200.engine import Engine
     torch.set_num_threads(min(32, os.cpu_count()))   # > 64 threads oversubscribe these small convs (measured 40x slower at 128)
-    eng = Engine(sd, image.shape[0], "cuda", dtype, reuse_memory=False)   # every intermediate tensor is kept
+    eng = Engine(sd, image.shape[0], "cuda", dtype, reuse_memory=False, widths=widths)   # every intermediate tensor is kept
     eng.run(image.cuda())
     torch.cuda.synchronize()
     rows = sweep(eng, sd, image, TOL[dtype])
@@ -121,6 +122,16 @@ def test_every_op_teacher_forced_16bit(sd, image, dtype):
 def test_every_op_teacher_forced_fp32_validation_plan(sd, image):
     """The fp32 validation plan (model_precision='fp32'): fp32 storage, fp64 accumulate."""
     _run(sd, image, torch.float32)
+
+
+def test_every_op_teacher_forced_hrnet_w48(image):
+    """The HRNet-W48 trunk of BASELINE configs[4]: the reference has no such network (parity unpinned: no golden can
+    exist), so every launch of its plan is pinned against the oracle's per-op restatement instead -- 48/96/192/384-
+    channel convs (zero-filled K tails, N split at 384 outputs), fuse layers, heads on the 50-channel coord concat."""
+    from acr_b200.netspec import WIDTHS_W48, build_acr_spec
+    from acr_b200.synth import synth_state_dict
+    sd48 = synth_state_dict(3, spec=build_acr_spec(512, widths=WIDTHS_W48))
+    _run(sd48, image, torch.bfloat16, widths=WIDTHS_W48)
 
 
 def test_heads_only_plan_teacher_forced(sd, image):
