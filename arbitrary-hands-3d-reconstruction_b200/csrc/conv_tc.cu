@@ -199,6 +199,7 @@ struct ConvTcParams {
   const void* res;
   void* out;
   int taps, ksz, stride, cchunks, cin_pad, npad, relu, has_res, out_f32, bias_per_image, pow11_ch0;
+  uint32_t bias_bytes;  // shared-memory bias region: 1 KB up to 256 output channels, more for the N-split layers beyond
   int nsplit, nsub;   // N split: every super-tile is computed as nsplit "virtual tiles" of nsub = npad / nsplit output channels
                       // (N = 256 would need all 512 TMEM columns for ONE tile: with two halves of 128 the accumulators are
                       // double buffered again and the epilogue of one half overlaps the MMAs of the other; also lifts N > 256)
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_base = base + P.b_region_bytes;
   const uint32_t stage_base = a_base + (uint32_t)SA * P.a_stage_bytes;  // epilogue staging: 2 halves x [128 px][128 B]
   const uint32_t bias_base = stage_base + P.stage_out_bytes;            // fp32 bias[npad] (<= 1 KB)
-  const uint32_t bar_base = bias_base + 1024u;
+  const uint32_t bar_base = bias_base + P.bias_bytes;
   // barrier map: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] bres tmem_full[buf][half] tmem_empty[buf][half] | tmem_ptr
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
@@ -967,7 +968,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
     const size_t b_tot = a.cout_pad <= 256 ? (size_t)a.k * a.k * (a.cin_pad / ck) * a.cout_pad * ck * 2 : (size_t)1 << 40;
     const size_t min_a0 = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * a_st;
     for (int nb = (nsub == 64 ? 1 : 3); nb >= 1 && !epi_nb; --nb) {
-      const size_t fx = 1024 + 1024 + 512 + (size_t)EPI_WARPS * nb * 4096;
+      const size_t fx = 1024 + (((size_t)a.cout_pad * 4 + 1023) & ~(size_t)1023) + 512 + (size_t)EPI_WARPS * nb * 4096;
       if (b_tot + min_a0 + fx <= (size_t)SMEM_BUDGET || 4 * b_blk + min_a0 + fx <= (size_t)SMEM_BUDGET) epi_nb = nb;
     }
     if (!epi_nb) want_staged = false;
@@ -1021,7 +1022,8 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   const size_t b_total = a.cout_pad <= 256 ? (size_t)p.taps * p.cchunks * a.cout_pad * ck * 2 : (size_t)1 << 40;
   p.tma_out = want_tma_out ? 1 : 0;
   p.stage_out_bytes = p.tma_out ? 2u * 16384u : (p.epi_staged ? (uint32_t)(EPI_WARPS * p.epi_nb) * 4096u : 0u);
-  const size_t fixed = 1024 /*alignment slack*/ + 1024 /*bias*/ + 512 /*barriers*/ + p.stage_out_bytes;
+  p.bias_bytes = (uint32_t)(((size_t)a.cout_pad * 4 + 1023) & ~(size_t)1023);
+  const size_t fixed = 1024 /*alignment slack*/ + p.bias_bytes + 512 /*barriers*/ + p.stage_out_bytes;
   const int nA = p.s2x ? 2 : (p.patch1 ? p.cchunks : (p.patch_mode ? p.cchunks * 3 : p.taps * p.cchunks));
   // stages that must fit next to resident weights: a tile's worth of kx patches (3) for 3x3 stride-1 convs, 2 otherwise
   const size_t min_a = (size_t)((p.patch_mode && !p.patch1) ? 3 : 2) * (size_t)p.a_stage_bytes;

@@ -3,6 +3,7 @@
 // :831-865 HigherResolutionNet.forward, :668-686 HighResolutionModule.forward) with a precompiled
 // schedule: tensor maps built once, branch-level concurrency on plan-internal streams, no Python
 // in the loop.  Also hosts the BN-folding weight packer.
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -222,10 +223,22 @@ extern "C" int acr_b200_plan_run(acr_b200_plan* p, const void* image, void* stre
   cudaStream_t main_st = static_cast<cudaStream_t>(stream);
   const int n = (int)p->ops.size();
   if (p->n_streams == 1) {
+    // ACR_B200_DEBUG_SYNC=1: synchronise after every launch and name the op that failed (debugging only)
+    static const bool debug_sync = [] { const char* e = getenv("ACR_B200_DEBUG_SYNC"); return e && atoi(e) != 0; }();
     for (int i = 0; i < n; ++i) {
       int rc = run_one(p->ops[i], p->batch, p->arena, p->weights,
                        static_cast<const char*>(image), p->act_dtype, p->tc[i], main_st);
       if (rc) return rc;
+      if (debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(main_st);
+        if (e != cudaSuccess) {
+          const acr_b200_op& o = p->ops[i];
+          set_error("plan op %d failed: %s (kind %d, in C %d %dx%d stride %d, out C %d %dx%d stride %d, k %d s %d cin_pad %d cout_pad %d res %d flags %d)",
+                    i, cudaGetErrorString(e), o.kind, o.in[0].C, o.in[0].H, o.in[0].W, o.in[0].pix_stride, o.out.C, o.out.H, o.out.W,
+                    o.out.pix_stride, o.k, o.stride, o.cin_pad, o.cout_pad, o.has_residual, o.shift[0]);
+          return ACR_B200_ECUDA;
+        }
+      }
     }
     return ACR_B200_OK;
   }
