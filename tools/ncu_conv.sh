@@ -20,9 +20,9 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
     python tools/profile_step.py --batch 256 > $OUT/prof_traffic.log 2>&1
 python tools/conv_traffic.py $OUT/conv_traffic_${TAG}.csv $OUT/conv_traffic_${TAG}.json
 [ "${FULL:-1}" = "1" ] || exit 0
-for MODE in 7 3; do
+for MODE in 23 19 34; do
   timeout 600 ncu --set full --import-source on --clock-control none --kernel-name-base demangled \
-      -k "regex:conv_tc_kernel<\(int\)64, __nv_bfloat16, \(int\)${MODE}>" -s 40 -c 1 -f \
+      -k "regex:conv_tc_kernel<\(int\)64, __nv_bfloat16, \(int\)${MODE}>" -s 12 -c 2 -f \
       -o $OUT/conv_tc_${TAG}_mode${MODE} python tools/profile_step.py --batch 256 > $OUT/prof_full_${MODE}.log 2>&1
 done
 ls -la $OUT | tail -5
