@@ -1,5 +1,5 @@
 """CPU: the committed ncu evidence under profiles/ and the tools that summarise it stay consistent
-(bench.py reads roofline.traffic from profiles/r1_conv_traffic.json)."""
+(bench.py reads roofline.traffic from the newest profiles/r*_conv_traffic.json whose kernel-build stamp matches)."""
 import json
 import os
 import subprocess
@@ -46,3 +46,41 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     r = json.load(open(os.path.join(ROOT, "profiles", "r1_final_bench_reference.json")))
     assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_round2_conv_traffic_and_tables_match_the_current_plan(tmp_path):
+    """The round-2 captures are of the current plan (341 conv launches: merged head stems)."""
+    dst = str(tmp_path / "t.json")
+    _run("tools/conv_traffic.py", "profiles/r2_final_conv_launches.csv", dst, env={"CONV_BUILD_ID": "x"})
+    got, ref = json.load(open(dst)), json.load(open(os.path.join(ROOT, "profiles", "r2_conv_traffic.json")))
+    for k in ("traffic_bytes", "algorithmic_bytes", "launches", "dram_read_bytes", "dram_write_bytes", "batch"):
+        assert got[k] == ref[k], k
+    assert ref["launches"] == 341 and len(ref["conv_build_id"]) == 12
+    assert 0.8 < ref["traffic_bytes"] / ref["algorithmic_bytes"] < 1.1
+    convs = _run("tools/layer_table.py", "convs", "profiles/r2_final_conv_launches.csv")
+    assert "over 341 launches" in convs
+    kernels = _run("tools/layer_table.py", "kernels", "profiles/r2_final_launches.csv")
+    for k in ("conv_tc_kernel<64, __nv_bfloat16, 23>", "conv_tc_kernel<64, __nv_bfloat16, 19>", "conv_tc_kernel<64, __nv_bfloat16, 34>",
+              "pool_kernel", "mano_forward_kernel", "fuse_kernel"):
+        assert k in kernels, k
+
+
+def test_round2_bench_lines_carry_the_contract_keys():
+    keys = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "roofline_mano", "mano_verts_max_abs_err")
+    for name, n in (("r2_final_bench_default.json", 1), ("r2_bench_2gpu_fused.json", 2), ("r2_bench_8gpu_fused.json", 8),
+                    ("r2_bench_8gpu_nccl.json", 8), ("r2_bench_fp16.json", 1), ("r2_bench_hrnet_w48.json", 1)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read())
+        for k in keys:
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["e2e"]["h2d_bytes_per_step"] == 256 * 512 * 512 * 3 and d["gpu_launches"] > 0
+        assert d["e2e"]["d2h_bytes_per_step"] > 512 * 778 * 3 * 4 + 512 * 21 * 3 * 4          # verts AND joints AND parameters
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert {"bound", "achieved", "peak", "unit", "frac", "at_65536_hands"} <= set(d["roofline_mano"])
+        assert d["mano_verts_max_abs_err"] < 1e-6
+        if n > 1:
+            assert d["gather_check"] is True and len(d["ms_per_step_by_rank"]) == n
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench_default.json")).read())
+    assert d["cpu_baseline"]["kind"] == "reference" and {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    r = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench_reference.json")).read())
+    assert r["impl"] == "reference" and r["cpu_baseline"]["kind"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
