@@ -6,27 +6,30 @@
 // reference dispatches to cuDNN + separate ATen elementwise kernels.
 //
 // GEMM view:  D[M = 128 output pixels][N = cout_pad] += A[M][K] * B[N][K],  K = taps * cin_pad.
-//   * M tile  = a 16(y) x 8(x) spatial patch of one image; one CTA computes ALL output channels of
-//     its patch (N <= 256 fits one UMMA instruction and <= 256 TMEM columns), so activations are
-//     never re-read across N tiles.
-//   * A operand: for filter tap (ky,kx) and channel chunk c0 the [128 x CK] slice is ONE 4-D TMA box
-//     {CK, 8, 16, 1} of the NHWC input at spatial offset (ky-1, kx-1); TMA's out-of-bounds zero
-//     fill IS the conv padding.  Stride-2 convs read four parity views (even/odd rows x cols) of the
-//     input, each with its own tensor map, so every tap is again a dense box.
-//   * B operand: packed weights [cout_pad][taps*cin_pad] (BN folded), one 2-D TMA box {CK, cout_pad}.
-//   * Both land in shared memory in the canonical K-major swizzled layout (128B / 64B / 32B swizzle
-//     for CK = 64 / 32 / 16) that UMMA shared-memory descriptors address directly.
-//   * 3x3 stride-1 convs use "patch mode": for each kx one 18(y) x 8(x) box is loaded and the three
-//     ky taps are three UMMA descriptors 8 rows (= one swizzle atom) apart inside it, so the input
-//     is pulled through L2 3.4x instead of 9x.
-//   * persistent CTAs (one per SM) loop over tiles; weights stay resident in shared memory when they
-//     fit (all 32/64-channel layers), otherwise they stream through their own mbarrier ring.
-//   * warp 0 = TMA producer; warps 1..2 = MMA issuers, ONE PER HALF of the 16x16 super-tile (each an elected
-//     thread issuing tcgen05.mma into its own fp32 accumulator in TMEM, double buffered): the issue rate of a
-//     single thread (a dependent stream of uniform-datapath instructions, ~72 clk per 128x64x16 MMA against 32
-//     clk of math) was the bound of the N = 64 layers, two independent issuers double it; 8 epilogue warps
-//     (tcgen05.ld -> +bias (+residual) (ReLU) -> 16-bit / fp32 NHWC) overlap the next tile's main loop.
-//     -DACR_DUAL_ISSUER=0 builds the single-issuer form (A/B measurements).
+//   * Work unit = a 16x16-pixel SUPER-TILE of one image = two M = 128 UMMA tiles (left / right 8 columns; an M tile is
+//     16 image rows x 8 pixels, i.e. 16 swizzle atoms of 8 pixels at a uniform stride).  One CTA computes all output
+//     channels of its tile (N <= 256 per instruction; wider layers and the MMA-bound 256->256 layers as "virtual tiles" of
+//     N / nsplit channels, ConvTcParams::nsplit), so activations are never re-read across N tiles.
+//   * A operand by TMA, the conv padding by TMA's out-of-bounds zero fill.  3x3 stride-1 convs with 64-channel chunks load
+//     ONE haloed box {64, 24, 18} per chunk and address all nine taps inside it through UMMA descriptors whose start is
+//     NOT aligned to the swizzle repeat (MODE_P1; the 128B swizzle follows the absolute shared-memory address, see
+//     tools/umma_shift_probe.cu); narrower chunks use three kx-shifted boxes {CK, 16, 18} with the ky taps as row offsets
+//     (MODE_PATCH).  Dense 32-channel tensors are convolved as x-pairs (two pixels per 128-byte row): stride 1 as a
+//     64->64 conv with block-sparse weights whose side taps are 32x32 corners (MODE_XPAIR), stride 2 from two row-parity
+//     boxes with taps = row offset + pair-column offset + K half (MODE_S2X).  Other stride-2 convs read four parity views
+//     (even/odd rows x columns, own tensor maps), 1x1 convs a single tap.
+//   * B operand: packed weights [cout_pad][taps*cin_pad] (BN folded), 2-D TMA boxes {CK, N}; resident in shared memory for
+//     the whole kernel when they fit (all 32/64-channel layers), otherwise streamed through their own mbarrier ring.
+//   * Both land in shared memory in the canonical K-major swizzled layout (128B / 64B / 32B swizzle for CK = 64 / 32 / 16)
+//     that UMMA shared-memory descriptors address directly.
+//   * Persistent CTAs (one per SM): warp 0 = TMA producer; warps 1..2 = MMA issuers, ONE PER HALF of the super-tile (each an
+//     elected thread issuing tcgen05.mma into its own fp32 accumulator in TMEM, double buffered when 4 N <= 512 columns);
+//     8 epilogue warps (tcgen05.ld -> +bias (+residual) (ReLU) -> 16-bit / fp32 NHWC) overlapping the next tile's main
+//     loop -- either with direct 256-bit global accesses or, where it measured faster (every layer with a residual, all
+//     N = 64 layers, wide convs of narrow inputs), STAGED: 4 KB slabs per warp, the residual prefetched by TMA loads and the
+//     result written by TMA stores, synchronised per warp only.
+//     -DACR_DUAL_ISSUER=0 builds the single-issuer form (A/B measurements; two issuers bought 6 %: the N = 64 MMAs are
+//     bound by the shared-memory bandwidth of their operand reads, profiles/r2_conv_ncu_summary.md).
 #include <cuda.h>
 #include <stdlib.h>
 

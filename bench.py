@@ -43,15 +43,23 @@ def load_peaks():
         return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def conv_build_id():
-    """sha1 of the conv kernel source: ncu-derived numbers under profiles/ are stamped with it, and dropped from
-    the bench line when the kernel has changed since (stale evidence must not be reported as current)."""
+def _code_digest(paths):
+    """sha1 over the CODE of the given sources: // comments, blank lines and indentation do not count, so editing a
+    comment does not orphan the ncu evidence that is stamped with this id."""
     import hashlib
     h = hashlib.sha1()
-    for f in ("conv_tc.cu", "plan.cu"):
-        with open(os.path.join(PKG, "csrc", f), "rb") as fh:
-            h.update(fh.read())
+    for path in paths:
+        with open(path) as fh:
+            for line in fh:
+                line = line.split("//")[0].strip()
+                if line:
+                    h.update(line.encode() + b"\n")
     return h.hexdigest()[:12]
+
+def conv_build_id():
+    """Digest of the conv kernel's code: ncu-derived numbers under profiles/ are stamped with it, and dropped from
+    the bench line when the kernel has changed since (stale evidence must not be reported as current)."""
+    return _code_digest([os.path.join(PKG, "csrc", f) for f in ("conv_tc.cu", "plan.cu")])
 
 
 def load_traffic(batch):

@@ -139,3 +139,40 @@ def test_plan_records_of_the_engine():
     assert len(c32) == 64                                  # the x-paired class: 32 BasicBlocks of branch 0
     old = Engine(None, 2, "cpu", dry_run=True, stem_on_tensor_cores=False)
     assert [r["kind"] for r in old.recs].count(L.OP_STEM) == 1 and old.n_ops == 368
+
+
+def test_s2x_weight_packing_places_each_tap_in_its_k_half(lib):
+    """ACR_CONV_S2X: a 3x3 stride-2 conv of a dense 32-channel tensor reads x-pairs (128-byte row = even pixel's
+    channels | odd neighbour's).  Tap (ky,kx) multiplies k-steps {0,1} (kx = 1: the even half) or {2,3} (kx = 0 / 2: the
+    odd half of pair ox-1 / pair ox), so the packed weights must carry its 32 input channels at K offset 32*(kx != 1) and
+    zeros in the other half (engine._pack_conv(s2x=True))."""
+    from acr_b200.engine import Engine, _Blob
+    rng = np.random.default_rng(6)
+    sd = {"c.weight": rng.standard_normal((48, 32, 3, 3)).astype(np.float32)}
+    eng = Engine(None, 1, "cpu", dry_run=True)
+    blob = _Blob()
+    w_off, _ = eng._pack_conv(sd, blob, "c", None, False, 64, 48, s2x=True)
+    wp = np.frombuffer(blob.tobytes(), np.uint16, count=48 * 9 * 64, offset=w_off).reshape(48, 3, 3, 64)     # [n][ky][kx][k]
+    ref = torch.from_numpy(sd["c.weight"]).bfloat16().view(torch.int16).numpy().view(np.uint16)              # [co][ci][ky][kx]
+    for kx in range(3):
+        used, unused = (slice(0, 32), slice(32, 64)) if kx == 1 else (slice(32, 64), slice(0, 32))
+        assert not wp[:, :, kx, unused].any()
+        assert (wp[:, :, kx, used] == ref[:, :, :, kx].transpose(0, 2, 1)).all()
+
+
+def test_merged_head_stems_concatenate_weights_and_slice_outputs():
+    """The eight head stems run as two N = 256 convs: slice j of the wide output must be conv j (weights / biases
+    concatenated along cout in order), its consumers read channel slices [64 j, 64 j + 64) of the 256-wide tensor, and
+    the registration order of the parameters (which the seeded weights and the goldens depend on) is the reference's."""
+    from acr_b200.engine import Engine
+    from acr_b200.netspec import build_acr_spec
+    a, b = build_acr_spec(512, merge_stems=True), build_acr_spec(512, merge_stems=False)
+    assert list(a.params.items()) == list(b.params.items())                  # same keys, shapes AND order
+    eng = Engine(None, 1, "cpu", dry_run=True)
+    merged = [r for r in eng.recs if r.get("attrs", {}).get("merged")]
+    assert [r["attrs"]["w"] for r in merged] == [[f"{s}_final_layers.{i}.0.0" for i in (1, 2, 3, 4)] for s in "lr"]
+    for r in merged:
+        wide = r["out"]
+        users = [q for q in eng.recs if any((t.base is wide) for t in q["ins"])]
+        assert sorted({t.c_off for q in users for t in q["ins"] if t.base is wide}) == [0, 64, 128, 192]
+        assert len(users) == 8                      # conv1 of the first BasicBlock and conv2's residual, per head

@@ -37,11 +37,9 @@ rd = sum(r["dram__bytes_read.sum"] for r in rows)
 wr = sum(r["dram__bytes_write.sum"] for r in rows)
 t = sum(r["gpu__time_duration.sum"] for r in rows)
 tp = sum(r["gpu__time_duration.sum"] * r.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) for r in rows) / t
-import hashlib
-_h = hashlib.sha1()
-for _f in ("conv_tc.cu", "plan.cu"):
-    _h.update(open(os.path.join(ROOT, "arbitrary-hands-3d-reconstruction_b200", "csrc", _f), "rb").read())
-out = {"conv_build_id": os.environ.get("CONV_BUILD_ID") or _h.hexdigest()[:12], "batch": batch, "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:conv_tc, batch {batch}, one step ({len(rows)} launches)",
+sys.path.insert(0, ROOT)
+import bench as _bench  # noqa: E402  (the stamp bench.py checks before it reports roofline.traffic)
+out = {"conv_build_id": os.environ.get("CONV_BUILD_ID") or _bench.conv_build_id(), "batch": batch, "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:conv_tc, batch {batch}, one step ({len(rows)} launches)",
        "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr, "algorithmic_bytes": alg, "launches": len(rows),
        "time_ms_under_ncu": t / 1e6, "tensor_pipe_active_pct_time_weighted": tp}
 json.dump(out, open(dst, "w"), indent=1)
