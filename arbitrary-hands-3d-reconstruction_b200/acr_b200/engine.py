@@ -117,8 +117,11 @@ class Engine:
         self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
         self.head_only = head_only
         from .netspec import WIDTHS
+        # (the folded fuse sums exist in the tensor-core conv only: the reference-conv and fp32 validation plans keep fuse ops)
         self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0",
-                                            widths=tuple(widths) if widths else WIDTHS)
+                                            widths=tuple(widths) if widths else WIDTHS,
+                                            fold_fuse=(os.environ.get("ACR_B200_FOLD_FUSE", "1") != "0"
+                                                       and act_dtype != torch.float32 and not debug_ref_conv))
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)
         self.debug_ref_conv = debug_ref_conv or self.f32
@@ -331,6 +334,10 @@ class Engine:
                 # (same rule for the wider trunks: 48 -> 64, 96 -> 128 with zero-filled tails)
                 o.cin_pad = _rup(x.C, 64) if x.C > 32 else _rup(x.C, 16)
                 o.cout_pad = _rup(r["out"].C, 16)
+                if a.get("extra"):
+                    o.shift[0] |= 16    # ACR_CONV_EXTRA: in_[1..] are further terms, nearest-upsampled by 2**shift[j]
+                    for q, (_, sh) in enumerate(a["extra"]):
+                        o.shift[1 + q] = sh
                 if "stem" in a:
                     # weights (64,3,3,3) OIHW -> (64, 32, 1, 1) with input channel (ky*3+kx)*3+ci; BN folded by pack_conv
                     w = f32(a["stem"]["w"] + ".weight")
@@ -350,15 +357,15 @@ class Engine:
                     weff[:, 112:115, 0, 0] = W[:, 0:3] + W[:, 109:112]
                     o.cin_pad = 128
                     o.w_offset[0] = self._pack_raw(blob, weff, o.cin_pad, o.cout_pad)
-                    o.shift[0] = 1      # ACR_CONV_BIAS_PER_IMAGE (aux[0] = bias_img from the part head)
+                    o.shift[0] |= 1     # ACR_CONV_BIAS_PER_IMAGE (aux[0] = bias_img from the part head)
                 elif s2x:
                     o.cin_pad = 64
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, o.cout_pad, s2x=True)
-                    o.shift[0] = 8      # ACR_CONV_S2X
+                    o.shift[0] |= 8     # ACR_CONV_S2X
                 elif pair:
                     o.cin_pad = o.cout_pad = 64
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], 64, 64, pair=True)
-                    o.shift[0] = 4      # ACR_CONV_XPAIR: side taps are 32x32 corners of the 64x64 block
+                    o.shift[0] |= 4     # ACR_CONV_XPAIR: side taps are 32x32 corners of the 64x64 block
                 elif a.get("merged"):
                     # convs of identical geometry on the same input: weights / biases concatenated along cout
                     each = a["merged"]
@@ -376,7 +383,7 @@ class Engine:
                 else:
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
                     if a.get("pow11"):
-                        o.shift[0] = 2  # ACR_CONV_POW11_CH0
+                        o.shift[0] |= 2  # ACR_CONV_POW11_CH0
             elif r["kind"] == L.OP_STEM:
                 w = f32(a["w"] + ".weight")                                   # (64,3,3,3) OIHW
                 g_, b_, m_, v_ = (f32(f"{a['bn']}.{n}") for n in ("weight", "bias", "running_mean", "running_var"))

@@ -74,7 +74,10 @@ class NetSpec:
     def conv(self, x: Tensor, wkey: str, bnkey: Optional[str], cout: int, k: int,
              s: int = 1, relu: bool = False, bias: bool = False,
              residual: Optional[Tensor] = None, out_dtype: str = "act",
-             out: Optional[Tensor] = None, hint: str = "", pow11: bool = False) -> Tensor:
+             out: Optional[Tensor] = None, hint: str = "", pow11: bool = False, defer: bool = False):
+        """``defer=True``: the parameters are registered HERE (registry order = the reference's construction order, which
+        the seeded weights and goldens depend on) but the op is returned instead of appended, for the caller to place
+        later in the schedule (-> (tensor, op))."""
         self._reg(wkey + ".weight", (cout, x.C, k, k), "conv_w")
         if bias:
             self._reg(wkey + ".bias", (cout,), "conv_b")
@@ -82,9 +85,12 @@ class NetSpec:
             self._reg_bn(bnkey, cout)
         Ho, Wo = x.H // s, x.W // s
         y = out if out is not None else self._t(cout, Ho, Wo, hint or wkey.split(".")[-1], out_dtype)
-        self.ops.append(Op("conv", y, [x] + ([residual] if residual is not None else []),
-                           dict(w=wkey, bn=bnkey, bias=bias, k=k, s=s, relu=relu,
-                                residual=residual is not None, pow11=pow11)))
+        op = Op("conv", y, [x] + ([residual] if residual is not None else []),
+                dict(w=wkey, bn=bnkey, bias=bias, k=k, s=s, relu=relu,
+                     residual=residual is not None, pow11=pow11))
+        if defer:
+            return y, op
+        self.ops.append(op)
         return y
 
     def reg_conv(self, wkey: str, bnkey: Optional[str], cout: int, cin: int, k: int, bias: bool) -> None:
@@ -147,7 +153,7 @@ def _bottleneck(g: NetSpec, x: Tensor, p: str, planes: int, down: bool) -> Tenso
 
 
 def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bool,
-               out0: Optional[Tensor] = None, WIDTHS: Tuple[int, ...] = None) -> List[Tensor]:
+               out0: Optional[Tensor] = None, WIDTHS: Tuple[int, ...] = None, fold_fuse: bool = False) -> List[Tensor]:
     # acr/model.py:571-686; 4 BasicBlocks per branch, then the fuse layers
     WIDTHS = WIDTHS or globals()["WIDTHS"]
     nb = len(xs)
@@ -158,6 +164,7 @@ def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bo
     outs = []
     for i in range(nb if multi_scale_output else 1):
         terms = []
+        folded = None      # (index in terms, deferred conv op): the sum of output i is folded into this conv's epilogue
         for j in range(nb):
             if j == i:
                 terms.append((xs[j], 0))
@@ -170,20 +177,38 @@ def _hr_module(g: NetSpec, prefix: str, xs: List[Tensor], multi_scale_output: bo
                 for k in range(i - j):
                     p = f"{prefix}.fuse_layers.{i}.{j}.{k}"
                     last = k == i - j - 1
-                    t = g.conv(t, p + ".0", p + ".1", WIDTHS[i] if last else WIDTHS[j], 3, s=2,
-                               relu=not last)
+                    if fold_fuse and last and j == i - 1:
+                        # the one-conv chain from the next finer branch: output i = relu(sum of terms) is computed in THIS
+                        # conv's epilogue (its own term never goes to memory), after every other term exists
+                        t, op = g.conv(t, p + ".0", p + ".1", WIDTHS[i], 3, s=2, relu=False, defer=True)
+                        folded = (len(terms), op)
+                    else:
+                        t = g.conv(t, p + ".0", p + ".1", WIDTHS[i] if last else WIDTHS[j], 3, s=2,
+                                   relu=not last)
                 terms.append((t, 0))
         # reference sums in order j = 0..nb-1 (acr/model.py:677-684)
-        outs.append(g.fuse(terms, relu=True, out=out0 if i == 0 else None))
+        if folded is None:
+            outs.append(g.fuse(terms, relu=True, out=out0 if i == 0 else None))
+        else:
+            pos, op = folded
+            others = [tm for q, tm in enumerate(terms) if q != pos]
+            op.ins = [op.ins[0]] + [t for t, _ in others]
+            op.attrs.update(relu=True, extra=[(t.name, sh) for t, sh in others], extra_pos=pos)
+            g.ops.append(op)
+            outs.append(op.out)
     return outs
 
 
 WIDTHS_W48 = (48, 96, 192, 384)
 
 
-def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tuple[int, ...] = WIDTHS) -> NetSpec:
+def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tuple[int, ...] = WIDTHS,
+                   fold_fuse: bool = True) -> NetSpec:
     """Full ACR network for one image of ``input_size`` x ``input_size``.  ``merge_stems=False`` keeps the eight
-    head stem convs as eight launches (A/B timing of the merged form).
+    head stem convs as eight launches (A/B timing of the merged form).  ``fold_fuse``: the fuse sums of the coarser
+    outputs (i >= 1) of every HighResolutionModule (acr/model.py:677-684) run in the epilogue of the stride-2 conv that
+    produces their term from the next finer branch: out_i = relu(conv(x_{i-1}) + sum of the other terms, nearest-
+    upsampled) -- that conv's output and a fuse launch per output disappear (15 of 23 fuse launches).
 
     ``widths``: branch widths of the HRNet trunk.  (32, 64, 128, 256) is the reference's network (the only one it
     contains: /root/reference/acr/model.py:796-797).  WIDTHS_W48 = (48, 96, 192, 384) is the HRNet-W48
@@ -211,12 +236,12 @@ def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tupl
     # ---- transition1 + stage2 (acr/model.py:796-805, 841-847)
     xs = [g.conv(x, "backbone.transition1.0.0", "backbone.transition1.0.1", W0, 3, relu=True),
           g.conv(x, "backbone.transition1.1.0.0", "backbone.transition1.1.0.1", W1, 3, s=2, relu=True)]
-    xs = _hr_module(g, "backbone.stage2.0", xs, True, WIDTHS=g.widths)
+    xs = _hr_module(g, "backbone.stage2.0", xs, True, WIDTHS=g.widths, fold_fuse=fold_fuse)
 
     # ---- transition2 + stage3 (4 modules, 3 branches)
     xs.append(g.conv(xs[-1], "backbone.transition2.2.0.0", "backbone.transition2.2.0.1", W2, 3, s=2, relu=True))
     for m in range(4):
-        xs = _hr_module(g, f"backbone.stage3.{m}", xs, True, WIDTHS=g.widths)
+        xs = _hr_module(g, f"backbone.stage3.{m}", xs, True, WIDTHS=g.widths, fold_fuse=fold_fuse)
 
     # ---- transition3 + stage4 (3 modules, 4 branches; last keeps only branch 0)
     xs.append(g.conv(xs[-1], "backbone.transition3.3.0.0", "backbone.transition3.3.0.1", W3, 3, s=2, relu=True))
@@ -227,7 +252,7 @@ def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tupl
     g.tensors[feat.name] = feat
     for m in range(3):
         last = m == 2
-        xs = _hr_module(g, f"backbone.stage4.{m}", xs, not last, out0=feat if last else None, WIDTHS=g.widths)
+        xs = _hr_module(g, f"backbone.stage4.{m}", xs, not last, out0=feat if last else None, WIDTHS=g.widths, fold_fuse=fold_fuse)
     x = xs[0]
     assert x is feat
     # coord channels 32,33 are constants written once (acr/model.py:52, 340-369)

@@ -196,6 +196,8 @@ struct ConvTcParams {
   CUtensorMap tmB;
   CUtensorMap tmOut;   // output as {C, W, H, B}, box {64, 8, 16, 1} (tma_out) or {64, 8, 4, 1} (epi_staged), 128B swizzle
   CUtensorMap tmRes;   // residual, box {64, 8, 4, 1}, 128B swizzle (epi_staged)
+  const void* ext[3];  // extra terms added before the activation (folded fuse sums), read at (oy >> shift, ox >> shift)
+  int n_ext, ext_shift[3], ext_stride[3], ext_W[3], ext_H[3];
   int epi_staged;      // N % 64 == 0, 16-bit output: every epilogue warp stages 32 px x 128 B slabs in shared memory, TMA in/out
   int epi_nb;          // staging buffers per epilogue warp (ring depth, 1..3)
   const float* bias;
@@ -766,6 +768,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
             }
           }
+          for (int e = 0; e < P.n_ext; ++e) {   // folded fuse sum: the other terms, nearest-upsampled (warp-uniform loop)
+            const T* xp = reinterpret_cast<const T*>(P.ext[e]) +
+                          (((size_t)n * P.ext_H[e] + (oy >> P.ext_shift[e])) * P.ext_W[e] + (ox >> P.ext_shift[e])) * P.ext_stride[e] + n_off + c0;
+            uint4 u0, u1;
+            ldg256(xp, u0, u1);
+            float x[16];
+            unpack8<T>(u0, x);
+            unpack8<T>(u1, x + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += x[i];
+          }
           if (P.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -960,7 +973,7 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   // staged epilogue (per-warp TMA store + TMA residual prefetch): N = 64, 16-bit output, shared bias
   const int epi_level = epi_staged_level();
   bool want_staged = !want_tma_out && a.out.dtype != ACR_DT_F32 && nsub % 64 == 0 && (uintptr_t)a.out.ptr % 16 == 0 &&
-                     a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 &&
+                     a.out.pix_stride % 8 == 0 && !a.bias_per_image && !a.pow11_ch0 && a.n_ext == 0 &&
                      (!a.has_res || ((uintptr_t)a.res.ptr % 16 == 0 && a.res.pix_stride % 8 == 0)) &&
                      (epi_level >= 2 || (epi_level == 1 && (a.has_res || a.cout_pad == 64 || (a.cout_pad >= 256 && a.cin_pad <= 64))));
   // ring depth per epilogue warp: one buffer when a tile is one slab (the next tile's MMAs hide the residual fetch),
@@ -994,6 +1007,13 @@ int conv_tc_prepare(const ConvArgs& a, int act_dtype, ConvTcPlan** out) {
   if (rc) { delete pl; return rc; }
   p.epi_staged = want_staged ? 1 : 0;
   p.epi_nb = epi_nb;
+  p.n_ext = a.n_ext;
+  for (int e = 0; e < a.n_ext; ++e) {
+    ACR_CHECK_ARG((uintptr_t)a.ext[e].ptr % 32 == 0 && a.ext[e].pix_stride % 16 == 0 && a.out.dtype != ACR_DT_F32,
+                  "conv_tc: extra term %d must be a 16-bit tensor with 32-byte aligned rows", e);
+    p.ext[e] = a.ext[e].ptr; p.ext_shift[e] = a.ext_shift[e]; p.ext_stride[e] = a.ext[e].pix_stride;
+    p.ext_W[e] = a.ext[e].W; p.ext_H[e] = a.ext[e].H;
+  }
   p.bias = a.bias; p.res = a.has_res ? a.res.ptr : nullptr; p.out = a.out.ptr;
   p.taps = a.k * a.k; p.ksz = a.k; p.stride = a.stride; p.cchunks = a.cin_pad / ck; p.cin_pad = a.cin_pad;
   p.ksteps = ck / 16;

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) conv_ref_kernel(ConvArgs a, long long tot
 
 int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st) {
   ACR_CHECK_ARG(a.cout_pad % 8 == 0 && a.cin_pad % 8 == 0 && a.in.pix_stride % 8 == 0, "conv_ref: alignment");
-  ACR_CHECK_ARG(!a.s2x, "conv_ref: the x-paired stride-2 form exists on the tensor-core path only");
+  ACR_CHECK_ARG(!a.s2x && a.n_ext == 0, "conv_ref: x-paired stride-2 inputs / folded fuse sums exist on the tensor-core path only");
   const long long total = (long long)a.batch * a.out.H * a.out.W * (a.cout_pad / 8);
   ACR_DISPATCH_ACT(act_dtype, conv_ref_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total));
   ACR_CHECK_LAUNCH();

@@ -16,6 +16,8 @@ struct ConvArgs {
   const float* bias;       // [cout_pad] (or [B][cout_pad] when bias_per_image)
   int k, stride, relu, has_res, cin_pad, cout_pad, bias_per_image, pow11_ch0, batch;
   int xpair;               // weights are the x-paired expansion of a 32->32 conv (ACR_CONV_XPAIR): side taps are 32x32 corners
+  TensorRef ext[3];        // ACR_CONV_EXTRA: up to three more terms added before the activation (HRNet fuse sums folded into
+  int n_ext, ext_shift[3]; // the producing conv): term e is read at pixel (oy >> shift, ox >> shift) = nearest upsampling
   int s2x;                 // ACR_CONV_S2X: 3x3 stride-2 conv of a dense 32-channel tensor given as its x-paired view (H, W/2, 64)
 };
 

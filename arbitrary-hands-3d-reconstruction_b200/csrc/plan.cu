@@ -39,6 +39,18 @@ static int make_conv_args(const acr_b200_op& op, int batch, char* arena, const c
   a->pow11_ch0 = (op.shift[0] & ACR_CONV_POW11_CH0) ? 1 : 0;
   a->xpair = (op.shift[0] & ACR_CONV_XPAIR) ? 1 : 0;
   a->s2x = (op.shift[0] & ACR_CONV_S2X) ? 1 : 0;
+  a->n_ext = 0;
+  if (op.shift[0] & ACR_CONV_EXTRA) {
+    ACR_CHECK_ARG(!op.has_residual && op.n_in >= 2 && op.n_in <= 4, "conv: extra terms need 2..4 inputs and no residual");
+    a->n_ext = op.n_in - 1;
+    for (int e = 0; e < a->n_ext; ++e) {
+      a->ext[e] = resolve(op.in[e + 1], arena, external);
+      a->ext_shift[e] = op.shift[e + 1];
+      ACR_CHECK_ARG(a->ext_shift[e] >= 0 && a->ext_shift[e] <= 3 && (a->ext[e].H << a->ext_shift[e]) == a->out.H &&
+                        (a->ext[e].W << a->ext_shift[e]) == a->out.W && a->ext[e].C == a->out.C && a->ext[e].dtype == a->out.dtype,
+                    "conv: extra term %d shape mismatch", e);
+    }
+  }
   if (a->bias_per_image) {
     ACR_CHECK_ARG(op.aux[0].dtype == ACR_DT_F32 && op.aux[0].pix_stride >= op.cout_pad, "conv: per-image bias tensor (aux[0]) malformed");
     a->bias = reinterpret_cast<const float*>(arena + op.aux[0].offset);

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) conv_f32_kernel(ConvArgs a, long long tot
 
 int launch_conv_f32(const ConvArgs& a, cudaStream_t st) {
   ACR_CHECK_ARG(a.cout_pad % 8 == 0 && a.cin_pad % 4 == 0 && a.in.pix_stride % 4 == 0 && a.in.dtype == ACR_DT_F32 &&
-                    a.out.dtype == ACR_DT_F32 && !a.xpair, "conv_f32: alignment / dtype");
+                    a.out.dtype == ACR_DT_F32 && !a.xpair && !a.s2x && a.n_ext == 0, "conv_f32: alignment / dtype / product-only forms");
   const long long total = (long long)a.batch * a.out.H * a.out.W * (a.cout_pad / 8);
   conv_f32_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
   ACR_CHECK_LAUNCH();

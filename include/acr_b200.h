@@ -201,7 +201,7 @@ enum {
   ACR_OP_FINALCONV = 9,   /* (retired)                                                          */
   ACR_OP_IM2COL_STEM = 10 /* uint8 NHWC image -> 3x3 s2 im2col of x/255*2-1, 27(+5 zero) 16-bit channels */
 };
-enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2, ACR_CONV_XPAIR = 4, ACR_CONV_S2X = 8 };
+enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2, ACR_CONV_XPAIR = 4, ACR_CONV_S2X = 8, ACR_CONV_EXTRA = 16 };
 enum { ACR_DT_BF16 = 0, ACR_DT_F16 = 1, ACR_DT_F32 = 2, ACR_DT_U8 = 3 };
 
 typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image extents)  */
@@ -223,6 +223,9 @@ typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image
  *            | ACR_CONV_XPAIR (3x3 s1 64->64 whose weights are the x-paired expansion of a 32->32 conv: channel =
  *            (x parity)*32 + c on a W/2 grid; the kx=0 / kx=2 taps are non-zero only in the [N 0..31][K 32..63] /
  *            [N 32..63][K 0..31] corner, which is all the kernel multiplies)
+ *            | ACR_CONV_EXTRA (in[1..n_in) are further terms of the same shape class as `out`, term j nearest-upsampled by
+ *            2**shift[j]: out = act(conv(in[0]) + bias + sum of terms) -- the fuse sum of HighResolutionModule.forward
+ *            (acr/model.py:677-684) folded into the conv that produces one of its terms; no residual then)
  *            | ACR_CONV_S2X (3x3 STRIDE-2 conv of a dense 32-channel tensor: in[0] is its x-paired view (H, W/2, 64) --
  *            even pixel's channels then the odd neighbour's in one 128-byte row -- `out` is (H/2, W/2); the packed
  *            weights [cout_pad][9][64] carry the 32 input channels of tap (ky,kx) at K offset 32*(kx != 1))

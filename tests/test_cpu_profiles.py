@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-R1_PLAN = {"ACR_B200_MERGE_STEMS": "0"}      # the round-1 captures are of the round-1 plan (eight separate head stems)
+R1_PLAN = {"ACR_B200_MERGE_STEMS": "0", "ACR_B200_FOLD_FUSE": "0"}   # the round-1 captures are of the round-1 plan
 
 
 def _run(*args, env=None):
@@ -51,7 +51,7 @@ def test_committed_bench_lines_carry_the_contract_keys():
 def test_round2_conv_traffic_and_tables_match_the_current_plan(tmp_path):
     """The round-2 captures are of the current plan (341 conv launches: merged head stems)."""
     dst = str(tmp_path / "t.json")
-    _run("tools/conv_traffic.py", "profiles/r2_final_conv_launches.csv", dst, env={"CONV_BUILD_ID": "x"})
+    _run("tools/conv_traffic.py", "profiles/r2_final_conv_launches.csv", dst, env={"CONV_BUILD_ID": "x"})     # the current plan
     got, ref = json.load(open(dst)), json.load(open(os.path.join(ROOT, "profiles", "r2_conv_traffic.json")))
     for k in ("traffic_bytes", "algorithmic_bytes", "launches", "dram_read_bytes", "dram_write_bytes", "batch"):
         assert got[k] == ref[k], k

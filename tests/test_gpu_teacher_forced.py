@@ -62,6 +62,11 @@ def sweep(eng, sd, image, tol):
                 for j, (wk, bk) in enumerate(zip(a["w"], a["bn"])):
                     checks.append((f"conv {wk} (slice {j} of a merged conv)", got[:, j * each:(j + 1) * each],
                                    op_ref.conv_bn_act(x, sdf, wk, bk, a["s"], a["relu"])))
+            elif a.get("extra"):           # a fuse sum folded into the conv that produces one of its terms
+                conv = op_ref.conv_bn_act(get(r["ins"][0]), sdf, a["w"], a["bn"], a["s"], False)
+                others, shifts, pos = [get(t) for t in r["ins"][1:]], [sh for _, sh in a["extra"]], a["extra_pos"]
+                exp = op_ref.fuse(others[:pos] + [conv] + others[pos:], shifts[:pos] + [0] + shifts[pos:], a["relu"])
+                checks.append((f"conv {a['w']} + folded fuse sum of {len(others) + 1} terms", get(r["out"]), exp))
             else:
                 res = get(r["ins"][1]) if a["residual"] else None
                 exp = op_ref.conv_bn_act(get(r["ins"][0]), sdf, a["w"], a["bn"], a["s"], a["relu"], res, a["pow11"])

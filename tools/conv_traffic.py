@@ -33,6 +33,7 @@ alg = 0
 for r in convs:
     x, y, at = r["ins"][0], r["out"], r["attrs"]
     alg += batch * x.H * x.W * x.C * 2 + batch * y.H * y.W * y.C * (4 if y.dtype == "f32" else 2) * (2 if at["residual"] else 1)
+    alg += sum(batch * t.H * t.W * t.C * 2 for t in r["ins"][1:]) if at.get("extra") else 0     # folded fuse terms, read once
 rd = sum(r["dram__bytes_read.sum"] for r in rows)
 wr = sum(r["dram__bytes_write.sum"] for r in rows)
 t = sum(r["gpu__time_duration.sum"] for r in rows)

@@ -55,6 +55,7 @@ else:
         a[3] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
         a[4] += ns * m.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
         a[5] += batch * (x.H * x.W * x.C * 2 + y.H * y.W * y.C * (4 if y.dtype == "f32" else 2) * (2 if at["residual"] else 1))
+        a[5] += sum(batch * t.H * t.W * t.C * 2 for t in r["ins"][1:]) if at.get("extra") else 0
     print("| cin | cout | k | s | H_in | res | n | total ms | avg us | TFLOP/s | DRAM GB/s (measured) | DRAM / algorithmic bytes | tensor pipe active |")
     print("|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
