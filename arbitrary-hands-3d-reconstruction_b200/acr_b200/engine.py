@@ -117,10 +117,12 @@ class Engine:
         self.stem_on_tensor_cores = stem_on_tensor_cores and not self.f32
         self.head_only = head_only
         from .netspec import WIDTHS
-        # (the folded fuse sums exist in the tensor-core conv only: the reference-conv and fp32 validation plans keep fuse ops)
+        # Folding the coarse fuse sums into the producing conv (ACR_B200_FOLD_FUSE=1) is an opt-in: measured on B200 it
+        # removes 0.97 ms of fuse kernels and adds 0.7-1.9 ms to the convs (the extra terms are latency-bound loads in
+        # the direct epilogue), i.e. no gain -- profiles/r2_bench_ab_fold_fuse.json.  Tensor-core plans only.
         self.spec: NetSpec = build_acr_spec(input_size, merge_stems=os.environ.get("ACR_B200_MERGE_STEMS", "1") != "0",
                                             widths=tuple(widths) if widths else WIDTHS,
-                                            fold_fuse=(os.environ.get("ACR_B200_FOLD_FUSE", "1") != "0"
+                                            fold_fuse=(os.environ.get("ACR_B200_FOLD_FUSE", "0") != "0"
                                                        and act_dtype != torch.float32 and not debug_ref_conv))
         self.input_size = input_size
         self.flops_per_image = conv_flops_per_image(self.spec)

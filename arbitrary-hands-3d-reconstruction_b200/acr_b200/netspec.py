@@ -203,12 +203,13 @@ WIDTHS_W48 = (48, 96, 192, 384)
 
 
 def build_acr_spec(input_size: int = 512, merge_stems: bool = True, widths: Tuple[int, ...] = WIDTHS,
-                   fold_fuse: bool = True) -> NetSpec:
+                   fold_fuse: bool = False) -> NetSpec:
     """Full ACR network for one image of ``input_size`` x ``input_size``.  ``merge_stems=False`` keeps the eight
     head stem convs as eight launches (A/B timing of the merged form).  ``fold_fuse``: the fuse sums of the coarser
     outputs (i >= 1) of every HighResolutionModule (acr/model.py:677-684) run in the epilogue of the stride-2 conv that
     produces their term from the next finer branch: out_i = relu(conv(x_{i-1}) + sum of the other terms, nearest-
-    upsampled) -- that conv's output and a fuse launch per output disappear (15 of 23 fuse launches).
+    upsampled) -- that conv's output and a fuse launch per output disappear (15 of 23 fuse launches).  Off by default:
+    measured neutral on B200 (the saved fuse kernels are paid back in the convs' epilogues).
 
     ``widths``: branch widths of the HRNet trunk.  (32, 64, 128, 256) is the reference's network (the only one it
     contains: /root/reference/acr/model.py:796-797).  WIDTHS_W48 = (48, 96, 192, 384) is the HRNet-W48

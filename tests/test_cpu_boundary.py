@@ -129,12 +129,15 @@ def test_plan_records_of_the_engine():
     # 348 Conv2d of the reference: conv1 runs as im2col + 1x1 (+1), the two contact_layers[4|5] convs are folded 1x1
     # launches (counted), the eight head stems run as two merged convs (-6)
     assert kinds.count(L.OP_CONV) == 341 and kinds.count(L.OP_IM2COL_STEM) == 1 and kinds.count(L.OP_STEM) == 0
-    # 23 fuse sums of the reference; the 15 of the coarser outputs run inside the stride-2 conv of their finer neighbour
-    assert kinds.count(L.OP_FUSE) == 8 and kinds.count(L.OP_POOL) == 1 and kinds.count(L.OP_PARTHEAD) == 1
-    assert eng.n_ops == len(kinds) == 354
-    folded = [r for r in eng.recs if r["kind"] == L.OP_CONV and r["attrs"].get("extra")]
-    assert len(folded) == 15 and all(r["attrs"]["s"] == 2 and r["attrs"]["relu"] and 2 <= len(r["ins"]) <= 4 for r in folded)
-    assert Engine(None, 2, "cpu", torch.float32, dry_run=True).n_ops == 354 + 15 - 1      # validation plan keeps the fuse ops
+    assert kinds.count(L.OP_FUSE) == 23 and kinds.count(L.OP_POOL) == 1 and kinds.count(L.OP_PARTHEAD) == 1
+    assert eng.n_ops == len(kinds) == 369
+    # opt-in (ACR_B200_FOLD_FUSE=1): the 15 fuse sums of the coarser outputs run inside the stride-2 conv of their finer neighbour
+    from acr_b200.netspec import build_acr_spec
+    spec = build_acr_spec(512, fold_fuse=True)
+    folded = [o for o in spec.ops if o.kind == "conv" and o.attrs.get("extra")]
+    assert sum(o.kind == "fuse" for o in spec.ops) == 8 and len(folded) == 15
+    assert all(o.attrs["s"] == 2 and o.attrs["relu"] and 2 <= len(o.ins) <= 4 for o in folded)
+    assert list(spec.params.items()) == list(eng.spec.params.items())          # same registry, same order
     assert eng.arena_bytes == 2 * 26 * 2 ** 20
     merged = [r for r in eng.recs if r["kind"] == L.OP_CONV and r["attrs"].get("merged")]
     assert len(merged) == 2 and all(r["out"].C == 256 and len(r["attrs"]["w"]) == 4 for r in merged)
@@ -142,7 +145,7 @@ def test_plan_records_of_the_engine():
            and r["ins"][0].C == 32 and r["out"].C == 32 and r["ins"][0].H == 128]
     assert len(c32) == 64                                  # the x-paired class: 32 BasicBlocks of branch 0
     old = Engine(None, 2, "cpu", dry_run=True, stem_on_tensor_cores=False)
-    assert [r["kind"] for r in old.recs].count(L.OP_STEM) == 1 and old.n_ops == 353
+    assert [r["kind"] for r in old.recs].count(L.OP_STEM) == 1 and old.n_ops == 368
 
 
 def test_s2x_weight_packing_places_each_tap_in_its_k_half(lib):

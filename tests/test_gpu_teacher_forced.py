@@ -124,6 +124,13 @@ def test_every_op_teacher_forced_16bit(sd, image, dtype):
     _run(sd, image, dtype)
 
 
+def test_every_op_teacher_forced_with_folded_fuse_sums(sd, image, monkeypatch):
+    """Opt-in plan (ACR_B200_FOLD_FUSE=1): the fuse sums of the coarser HR-module outputs computed in the epilogue of the
+    stride-2 conv that produces one of their terms (extra terms nearest-upsampled in the epilogue)."""
+    monkeypatch.setenv("ACR_B200_FOLD_FUSE", "1")
+    _run(sd, image, torch.bfloat16)
+
+
 def test_every_op_teacher_forced_fp32_validation_plan(sd, image):
     """The fp32 validation plan (model_precision='fp32'): fp32 storage, fp64 accumulate."""
     _run(sd, image, torch.float32)
