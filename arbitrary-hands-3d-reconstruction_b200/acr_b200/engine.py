@@ -228,6 +228,10 @@ class Engine:
                 recs.append(dict(kind=L.OP_CONV_REF if self.debug_ref_conv else L.OP_CONV, out=op.out,
                                  ins=[op.ins[1]], aux=[bias_img[s]],
                                  attrs=dict(k=1, s=1, relu=False, residual=False, pow11=False, fold_side=s)))
+            elif op.kind == "stem" and self.stem_on_tensor_cores and not self.debug_ref_conv \
+                    and os.environ.get("ACR_B200_STEM_FUSED", "1") != "0":
+                # conv1 + bn1 + relu as ONE tcgen05 GEMM whose im2col operand is built in shared memory (csrc/stem_tc.cu)
+                recs.append(dict(kind=L.OP_STEM_TC, out=op.out, ins=[op.ins[0]], attrs=dict(stem=op.attrs)))
             elif op.kind == "stem" and self.stem_on_tensor_cores:
                 # conv1 + bn1 + relu as im2col (27 normalised taps -> 32 channels) + a 1x1 tcgen05 conv
                 cols = Tensor("stem_im2col", 32, op.out.H, op.out.W, "act")
@@ -386,6 +390,15 @@ class Engine:
                     o.w_offset[0], o.w_offset[1] = self._pack_conv(sd, blob, a["w"], a["bn"], a["bias"], o.cin_pad, o.cout_pad)
                     if a.get("pow11"):
                         o.shift[0] |= 2  # ACR_CONV_POW11_CH0
+            elif r["kind"] == L.OP_STEM_TC:
+                # weights (64,3,3,3) OIHW -> (64, 32, 1, 1) with input channel (ky*3+kx)*3+ci; BN folded by pack_conv
+                w = f32(a["stem"]["w"] + ".weight")
+                w1 = np.zeros((64, 32, 1, 1), np.float32)
+                w1[:, :27, 0, 0] = w.transpose(0, 2, 3, 1).reshape(64, 27)
+                sd_stem = {"stem.weight": w1}
+                for nme in ("weight", "bias", "running_mean", "running_var"):
+                    sd_stem[f"stembn.{nme}"] = f32(f"{a['stem']['bn']}.{nme}")
+                o.w_offset[0], o.w_offset[1] = self._pack_conv(sd_stem, blob, "stem", "stembn", False, 32, 64)
             elif r["kind"] == L.OP_STEM:
                 w = f32(a["w"] + ".weight")                                   # (64,3,3,3) OIHW
                 g_, b_, m_, v_ = (f32(f"{a['bn']}.{n}") for n in ("weight", "bias", "running_mean", "running_var"))

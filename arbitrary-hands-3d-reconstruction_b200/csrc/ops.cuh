@@ -30,6 +30,10 @@ struct FuseArgs {
 int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, const float* bias, int batch,
                 int act_dtype, cudaStream_t st);
 int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st);
+// stem conv on the tensor cores with the A operand built in shared memory from the uint8 frame (stem_tc.cu): w = packed
+// [64][32] 16-bit (tap-major K, BN folded), bias fp32 [64]
+int launch_stem_tc(const TensorRef& img, const TensorRef& out, const void* w, const float* bias, int batch, int act_dtype,
+                   cudaStream_t st);
 int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st);
 int launch_fuse(const FuseArgs& a, int act_dtype, cudaStream_t st);
 int launch_bilinear2x(const TensorRef& in, const TensorRef& out, int batch, int act_dtype, cudaStream_t st);

@@ -110,6 +110,10 @@ static int run_one(const acr_b200_op& op, int batch, char* arena, const char* we
                          reinterpret_cast<const float*>(weights + op.w_offset[0]),
                          reinterpret_cast<const float*>(weights + op.w_offset[1]), batch, act_dtype, st);
     }
+    case ACR_OP_STEM_TC:
+      ACR_CHECK_ARG(external != nullptr, "stem_tc: external image pointer is null");
+      return launch_stem_tc(resolve(op.in[0], arena, external), resolve(op.out, arena, external), weights + op.w_offset[0],
+                            reinterpret_cast<const float*>(weights + op.w_offset[1]), batch, act_dtype, st);
     case ACR_OP_IM2COL_STEM:
       ACR_CHECK_ARG(external != nullptr, "im2col_stem: external image pointer is null");
       return launch_im2col_stem(resolve(op.in[0], arena, external), resolve(op.out, arena, external), batch, act_dtype, st);

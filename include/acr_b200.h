@@ -199,7 +199,8 @@ enum {
   ACR_OP_PARTHEAD = 7,    /* merge partials + LocallyConnected2d + Linear + per-image bias      */
   ACR_OP_CONV_REF = 8,    /* debug: same contract as ACR_OP_CONV on CUDA cores (tests only)     */
   ACR_OP_FINALCONV = 9,   /* (retired)                                                          */
-  ACR_OP_IM2COL_STEM = 10 /* uint8 NHWC image -> 3x3 s2 im2col of x/255*2-1, 27(+5 zero) 16-bit channels */
+  ACR_OP_IM2COL_STEM = 10, /* uint8 NHWC image -> 3x3 s2 im2col of x/255*2-1, 27(+5 zero) 16-bit channels */
+  ACR_OP_STEM_TC = 11      /* STEM on the tensor cores: the im2col operand is built in shared memory, never in HBM   */
 };
 enum { ACR_CONV_BIAS_PER_IMAGE = 1, ACR_CONV_POW11_CH0 = 2, ACR_CONV_XPAIR = 4, ACR_CONV_S2X = 8, ACR_CONV_EXTRA = 16 };
 enum { ACR_DT_BF16 = 0, ACR_DT_F16 = 1, ACR_DT_F32 = 2, ACR_DT_U8 = 3 };
@@ -214,6 +215,9 @@ typedef struct acr_b200_tensor {  /* NHWC activation inside the arena (per-image
 
 /* One launch.  Which fields are read depends on `kind`:
  *  STEM      in[0]=image(u8,external) out; w_offset[0]=fp32 [27][64] folded weights, [1]=fp32 bias[64]
+ *  STEM_TC   in[0]=image(u8,external) out (64 ch, H/2 x W/2, 16-bit); w_offset[0]=packed [64][32] 16-bit weights (input
+ *            channel (ky*3+kx)*3+ci, 27..31 zero, BN folded), [1]=fp32 bias[64]: conv1 + bn1 + ReLU of acr/model.py:832-835
+ *            as one tcgen05 GEMM whose A operand (the 27 normalised taps of every output pixel) is built in shared memory
  *  IM2COL_STEM in[0]=image(u8,external) out (32 ch, H/2 x W/2): channel (ky*3+kx)*3+ci = normalised tap,
  *            0 outside the image; the stem conv then runs as a 1x1 CONV on the tensor cores
  *  CONV(_REF) in[0]=x, in[1]=residual (has_residual) out; w_offset[0]=packed 16-bit weights

@@ -73,6 +73,8 @@ def sweep(eng, sd, image, tol):
                 checks.append((f"conv {a['w']} k{a['k']} s{a['s']}", get(r["out"]), exp))
         elif kind == L.OP_STEM:
             checks.append(("stem (CUDA-core form)", get(r["out"]), op_ref.stem(image, sdf)))
+        elif kind == L.OP_STEM_TC:
+            checks.append(("stem (tcgen05, operand built in shared memory)", get(r["out"]), op_ref.stem(image, sdf)))
         elif kind == L.OP_IM2COL_STEM:
             checks.append(("im2col of the normalised frame", get(r["out"])[:, :27], op_ref.im2col_stem(image)))
         elif kind == L.OP_FUSE:
