@@ -20,6 +20,10 @@ POOL_CHUNKS = 16
 POOL_PART_FLOATS = 256 * 32 + 64
 
 
+def _pow2(v):
+    return v > 0 and (v & (v - 1)) == 0
+
+
 def _rup(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -229,7 +233,7 @@ class Engine:
                                  ins=[op.ins[1]], aux=[bias_img[s]],
                                  attrs=dict(k=1, s=1, relu=False, residual=False, pow11=False, fold_side=s)))
             elif op.kind == "stem" and self.stem_on_tensor_cores and not self.debug_ref_conv \
-                    and os.environ.get("ACR_B200_STEM_FUSED", "1") != "0":
+                    and os.environ.get("ACR_B200_STEM_FUSED", "1") != "0" and _pow2(op.out.W // 16) and _pow2(op.out.H // 16):
                 # conv1 + bn1 + relu as ONE tcgen05 GEMM whose im2col operand is built in shared memory (csrc/stem_tc.cu)
                 recs.append(dict(kind=L.OP_STEM_TC, out=op.out, ins=[op.ins[0]], attrs=dict(stem=op.attrs)))
             elif op.kind == "stem" and self.stem_on_tensor_cores:

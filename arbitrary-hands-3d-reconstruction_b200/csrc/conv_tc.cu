@@ -864,6 +864,16 @@ static int encode(CUtensorMap* m, int act_dtype, int rank, const void* ptr, cons
   return ACR_B200_OK;
 }
 
+// Output tensor map of the staged epilogues: NHWC tensor as {C, W, H, B}, box {64 channels, 8 px, 4 rows, 1}, 128B swizzle
+// (one epilogue warp's 32-pixel slab).  Shared with stem_tc.cu.
+int encode_slab_store_map(void* tmap, const TensorRef& out, int channels, int batch, int act_dtype) {
+  const cuuint64_t esz = 2;
+  cuuint32_t box[4] = {64, 8, 4, 1};
+  cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)out.W, (cuuint64_t)out.H, (cuuint64_t)batch};
+  cuuint64_t str[3] = {(cuuint64_t)out.pix_stride * esz, (cuuint64_t)out.W * out.pix_stride * esz, (cuuint64_t)out.H * out.W * out.pix_stride * esz};
+  return encode(static_cast<CUtensorMap*>(tmap), act_dtype, 4, out.ptr, dims, str, box, 64);
+}
+
 // The TMA-store epilogue is opt-in (ACR_B200_TMA_OUT=1, read at plan creation): on B200 it measured 2 % slower per
 // step than direct 256-bit stores (two named barriers per slab and one A stage less outweigh the saved LSU
 // wavefronts), see DESIGN.md section 6.  It stays as a tested path for wider-N / store-bound layers.

@@ -32,6 +32,8 @@ int launch_stem(const TensorRef& img, const TensorRef& out, const float* w, cons
 int launch_im2col_stem(const TensorRef& img, const TensorRef& out, int batch, int act_dtype, cudaStream_t st);
 // stem conv on the tensor cores with the A operand built in shared memory from the uint8 frame (stem_tc.cu): w = packed
 // [64][32] 16-bit (tap-major K, BN folded), bias fp32 [64]
+// conv_tc.cu: tensor map (128 bytes, 64-byte aligned) for TMA stores of [4 rows][8 px][64 ch] slabs into an NHWC tensor
+int encode_slab_store_map(void* tmap, const TensorRef& out, int channels, int batch, int act_dtype);
 int launch_stem_tc(const TensorRef& img, const TensorRef& out, const void* w, const float* bias, int batch, int act_dtype,
                    cudaStream_t st);
 int launch_conv_ref(const ConvArgs& a, int act_dtype, cudaStream_t st);

@@ -11,8 +11,8 @@
 // Persistent CTAs, one per SM, tile = 16x16 output pixels (two M = 128 UMMA tiles: left / right 8 columns):
 //   warps 0..7   epilogue: tcgen05.ld -> +bias -> ReLU -> 16-bit NHWC, 256-bit stores        (warp & 3 = TMEM lane quadrant)
 //   warp  8      MMA issuer: one elected thread, 2 k-steps x 2 halves of M=128 N=64 K=16 per tile, fp32 accumulators in TMEM
-//   warps 9..16  producers: thread = output pixel; stage the 33x33 uint8 patch of the tile in shared memory (coalesced),
-//                look the 27 taps up in a 256-entry table of (float)v / 255.f * 2.f - 1.f (bit-identical to the reference's
+//   warps 9..16  producers: thread = output pixel; read its 27 uint8 taps from the frame (L1 shares them between neighbours),
+//                look them up in a 256-entry table of (float)v / 255.f * 2.f - 1.f (bit-identical to the reference's
 //                normalisation), round to the storage type, write the swizzled 64-byte row; generic -> async proxy fence,
 //                producer-only named barrier, one mbarrier arrive per stage.
 #include <cuda.h>
@@ -49,6 +49,10 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t* r) {
                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // K-major SWIZZLE_64B descriptor: start >> 4 | LBO (unused) | SBO | version 1 | layout 4
 __device__ __forceinline__ uint64_t desc64(uint32_t saddr, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
@@ -57,17 +61,19 @@ __device__ __forceinline__ uint64_t desc64(uint32_t saddr, uint32_t sbo) {
 constexpr int NS = 4;                       // operand stages
 constexpr int EPI = 8, PROD_WARPS = 8;
 constexpr int THREADS = 32 * (EPI + 1 + PROD_WARPS);
-constexpr int PATCH_ROW = 112;              // bytes per staged patch row (33 pixels x 3 = 99, padded)
 constexpr int A_BYTES = 256 * 64;           // one stage of the A operand: 256 pixel rows x 64 B
-constexpr int PATCH_BYTES = 33 * PATCH_ROW;
-constexpr int SMEM = 1024 + NS * A_BYTES + 4096 /*weights*/ + NS * PATCH_BYTES + 1024 /*lut*/ + 256 /*bias*/ + 256 /*barriers*/;
+constexpr int SLAB = 4096;                  // one epilogue warp's 32 pixels x 64 channels, the box of a TMA store
+constexpr int OUT_BYTES = EPI * 2 * SLAB;   // two slabs per epilogue warp
+constexpr int SMEM = 1024 + NS * A_BYTES + 4096 /*weights*/ + OUT_BYTES + 1024 /*lut*/ + 256 /*bias*/ + 256 /*barriers*/;
 
 struct StemTcParams {
+  CUtensorMap tmOut;      // output as {64, W/2, H/2, B}, box {64, 8, 4, 1}, 128B swizzle
   const uint8_t* img;     // (B, H, W, 3) uint8
   void* out;              // (B, H/2, W/2, out_stride) 16-bit
   const void* w;          // packed [64][32] 16-bit, K-major (channel (ky*3+kx)*3+ci, 27..31 zero), BN folded
   const float* bias;      // [64]
-  int H, W, out_stride, tiles_x, tiles_per_img, total_tiles;
+  int H, W, out_stride, total_tiles;
+  int tx_log2, tpi_log2;  // tiles per output row / per image are powers of two (512 x 512 frames: 16, 256): shifts, no divisions in the tile loops
   uint32_t idesc;
 };
 
@@ -79,8 +85,8 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
   uint8_t* gen = raw_smem + (base - raw);                 // generic pointer to the aligned base
   const uint32_t a_base = base;
   const uint32_t w_base = base + NS * A_BYTES;
-  uint8_t* patch = gen + NS * A_BYTES + 4096;
-  float* lut = reinterpret_cast<float*>(gen + NS * A_BYTES + 4096 + NS * PATCH_BYTES);
+  const uint32_t out_base = base + NS * A_BYTES + 4096;     // 1024-aligned: the 128B swizzle of the slabs follows the address
+  float* lut = reinterpret_cast<float*>(gen + NS * A_BYTES + 4096 + OUT_BYTES);
   float* s_bias = lut + 256;
   const uint32_t bar_base = s32(s_bias + 64);
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -115,14 +121,13 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
 
   if (warp < EPI) {
     // ===================================================================================== epilogue
-    const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
+    const int q = warp & 3, h = warp >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)it >> 1;
-      const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
-      const int oy = (rem / P.tiles_x) * 16 + (r >> 3), ox = (rem % P.tiles_x) * 16 + h * 8 + (r & 7);
-      const size_t pix = ((size_t)n * (P.H / 2) + oy) * (P.W / 2) + ox;
+      const int n = tile >> P.tpi_log2, rem = tile & ((1 << P.tpi_log2) - 1);
+      const int ty = (rem >> P.tx_log2) * 16 + 4 * q, tx = (rem & ((1 << P.tx_log2) - 1)) * 16 + h * 8;   // slab origin
       mb_wait(tfull(buf), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + h) * 64);
@@ -132,16 +137,29 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mb_arrive(tempty(buf));
-      T* o = reinterpret_cast<T*>(P.out) + pix * P.out_stride;
+      if (lane == 0) {
+        mb_arrive(tempty(buf));
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this slab has read it
+      }
+      __syncwarp();
+      // lane = pixel (row lane >> 3, column lane & 7) of the slab = 128-byte line `lane`: chunk c lives at c ^ (lane & 7)
+      const uint32_t slab = out_base + (uint32_t)(warp * 2 + (it & 1)) * SLAB, row = slab + (uint32_t)lane * 128u;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[c][i]) + s_bias[c * 16 + i], 0.f);
-        stg256(o + c * 16, pack8<T>(f), pack8<T>(f + 8));
+        sts128(row + (((uint32_t)(2 * c) ^ (uint32_t)(lane & 7)) << 4), pack8<T>(f));
+        sts128(row + (((uint32_t)(2 * c + 1) ^ (uint32_t)(lane & 7)) << 4), pack8<T>(f + 8));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&P.tmOut, slab, 0, tx, ty, n);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the slabs must outlive the stores
   } else if (warp == EPI) {
     // =================================================================================== MMA issuer
     if (elect_one()) {
@@ -171,51 +189,49 @@ __global__ void __launch_bounds__(THREADS, 1) stem_tc_kernel(const __grid_consta
     const int py = t >> 4, px = t & 15;
     int s = 0;
     uint32_t ph = 0;
+    const int r = py * 16 + px;
+    const int sw = (r >> 1) & 3;
+    const int tmask = (1 << P.tpi_log2) - 1, xmask = (1 << P.tx_log2) - 1;
+    const size_t img_bytes = (size_t)P.H * P.W * 3;
+    // Only the top and the left frame edges pad (the patch of tile (y0, x0) starts at input pixel (2*y0 - 1, 2*x0 - 1) and ends
+    // inside the frame): filter row 0 of pixel row 0 of the tiles with y0 == 0, filter column 0 of pixel column 0 where x0 == 0.
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int n = tile / P.tiles_per_img, rem = tile % P.tiles_per_img;
-      const int y0 = (rem / P.tiles_x) * 16, x0 = (rem % P.tiles_x) * 16;
-      const int iy0 = 2 * y0 - 1, ix0 = 2 * x0 - 1;                       // input pixel of patch (0, 0)
-      mb_wait(emptyA(s), ph ^ 1u);                                         // the MMAs that read this stage are done
-      uint8_t* pp = patch + s * PATCH_BYTES;
-      // ---- stage the 33 x 33 x 3 uint8 patch (rows of 99 contiguous bytes of the frame)
-      const uint8_t* img = P.img + (size_t)n * P.H * P.W * 3;
-      for (int i = t; i < 33 * 25; i += 256) {                             // 25 4-byte words per row (100 >= 99 bytes)
-        const int r = i / 25, wq = i - r * 25;
-        const int iy = iy0 + r;
-        uint32_t word = 0;
-        if (iy >= 0 && iy < P.H) {
-          const long long rowoff = ((long long)iy * P.W) * 3;
-          const int b0 = ix0 * 3 + wq * 4;                                 // byte offset inside the image row (may be < 0)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int bb = b0 + k;
-            const uint32_t v = (bb >= 0 && bb < P.W * 3) ? (uint32_t)img[rowoff + bb] : 0u;
-            word |= v << (8 * k);
-          }
+      const int n = tile >> P.tpi_log2, rem = tile & tmask;
+      const int y0 = (rem >> P.tx_log2) * 16, x0 = (rem & xmask) * 16;
+      const bool pad_top = (y0 | py) == 0, pad_left = (x0 | px) == 0;
+      const int iy = 2 * (y0 + py) - (pad_top ? 0 : 1), ix = 2 * (x0 + px) - (pad_left ? 0 : 1);   // first tap that exists
+      const uint8_t* p0 = P.img + (size_t)n * img_bytes + ((size_t)iy * P.W + ix) * 3;
+      {  // pull the NEXT tile's 33 x 99-byte patch towards L1 while this one is converted
+        const int nt = tile + (int)gridDim.x;
+        if (nt < P.total_tiles && t < 66) {
+          const int nrem = nt & tmask;
+          int piy = 2 * (nrem >> P.tx_log2) * 16 - 1 + (t >> 1), pix = 2 * (nrem & xmask) * 16 - 1;
+          piy = piy < 0 ? 0 : piy; pix = pix < 0 ? 0 : pix;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.img + (size_t)(nt >> P.tpi_log2) * img_bytes + ((size_t)piy * P.W + pix) * 3 + (t & 1) * 96));
         }
-        *reinterpret_cast<uint32_t*>(pp + r * PATCH_ROW + wq * 4) = word;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");                        // producers only
-      // ---- this thread's pixel: 27 taps -> 32 channels -> one swizzled 64-byte row
+      mb_wait(emptyA(s), ph ^ 1u);                                         // the MMAs that read this stage are done
+      // ---- this thread's pixel: 3 filter rows x 9 contiguous bytes straight from the frame (neighbouring pixels share them
+      // through L1); a padded row / column reads the next one instead (always inside the frame) and is zeroed afterwards
+      uint32_t raw9[3][9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const uint8_t* prow = p0 + (size_t)(pad_top ? (ky ? ky - 1 : 0) : ky) * P.W * 3 - (pad_left ? 3 : 0);
+        const uint8_t* pcol0 = prow + (pad_left ? 3 : 0);                   // filter column 0 (or its stand-in)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) raw9[ky][j] = (uint32_t)__ldg((j < 3 ? pcol0 : prow) + j);
+      }
       float vch[32];
 #pragma unroll
       for (int i = 27; i < 32; ++i) vch[i] = 0.f;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = iy0 + 2 * py + ky;
-        const bool yok = iy >= 0 && iy < P.H;
-        const uint8_t* prow = pp + (2 * py + ky) * PATCH_ROW + (2 * px) * 3;
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = ix0 + 2 * px + kx;
-          const bool ok = yok && ix >= 0 && ix < P.W;
-#pragma unroll
-          for (int ci = 0; ci < 3; ++ci) vch[(ky * 3 + kx) * 3 + ci] = ok ? lut[prow[kx * 3 + ci]] : 0.f;
+        for (int j = 0; j < 9; ++j) {
+          const float v = lut[raw9[ky][j]];
+          vch[ky * 9 + j] = (ky == 0 && j < 3) ? ((pad_top || pad_left) ? 0.f : v) : ky == 0 ? (pad_top ? 0.f : v) : j < 3 ? (pad_left ? 0.f : v) : v;
         }
-      }
-      const int r = py * 16 + px;
       uint8_t* arow = gen + s * A_BYTES + r * 64;
-      const int sw = (r >> 1) & 3;
 #pragma unroll
       for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(arow + ((c ^ sw) << 4)) = pack8<T>(vch + c * 8);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> visible to the tensor core
@@ -240,9 +256,15 @@ int launch_stem_tc(const TensorRef& img, const TensorRef& out, const void* w, co
                     out.W % 16 == 0 && out.pix_stride % 16 == 0 && (uintptr_t)out.ptr % 32 == 0 && (uintptr_t)w % 16 == 0 &&
                     out.dtype == act_dtype, "stem_tc: shape / alignment");
   StemTcParams p;
+  {
+    const int rc = encode_slab_store_map(&p.tmOut, out, 64, batch, act_dtype);
+    if (rc) return rc;
+  }
   p.img = static_cast<const uint8_t*>(img.ptr); p.out = out.ptr; p.w = w; p.bias = bias;
   p.H = img.H; p.W = img.W; p.out_stride = out.pix_stride;
-  p.tiles_x = out.W / 16; p.tiles_per_img = p.tiles_x * (out.H / 16); p.total_tiles = p.tiles_per_img * batch;
+  const int tiles_x = out.W / 16, tiles_per_img = tiles_x * (out.H / 16);
+  ACR_CHECK_ARG((tiles_x & (tiles_x - 1)) == 0 && (tiles_per_img & (tiles_per_img - 1)) == 0, "stem_tc: tiles per row / image must be powers of two");
+  p.tx_log2 = __builtin_ctz(tiles_x); p.tpi_log2 = __builtin_ctz(tiles_per_img); p.total_tiles = tiles_per_img * batch;
   const uint32_t fmt = act_dtype == ACR_DT_BF16 ? 1u : 0u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   int dev = 0, sms = 148;
