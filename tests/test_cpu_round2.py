@@ -151,3 +151,22 @@ def test_lazy_outputs_refuse_stale_maps():
     with pytest.raises(RuntimeError):
         out["l_center_map"]
     assert LazyOutputs(None)["segms"] is None                   # return_maps=False
+
+
+def test_stem_normalisation_formula_is_bit_exact():
+    """csrc/stem_tc.cu `normalised()`: x = byte as fp32, q = fma(x, rh, x * rl), out = fma(q, 2, -1) must equal the
+    reference's (float)b / 255.f * 2.f - 1.f (acr/model.py:832) for every byte, bit for bit.  fp64 emulates each fma
+    exactly here (24-bit x 24-bit products and their sums with one more fp32 fit in 53 bits)."""
+    f32, f64 = np.float32, np.float64
+    rh = np.uint32(0x3B808081).view(f32)
+    rl = np.uint32(0xAF7EFEFF).view(f32)
+    b = np.arange(256, dtype=np.uint32)
+    x = ((b | np.uint32(0x4B000000)).view(f32) - f32(8388608.0)).astype(f32)
+    assert np.array_equal(x, b.astype(f32))
+    t = (x * rl).astype(f32)
+    q = (x.astype(f64) * f64(rh) + t.astype(f64)).astype(f32)
+    out = (q.astype(f64) * 2.0 - 1.0).astype(f32)
+    ref = b.astype(f32) / f32(255.0) * f32(2.0) - f32(1.0)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    src = open(os.path.join(ROOT, "arbitrary-hands-3d-reconstruction_b200", "csrc", "stem_tc.cu")).read()
+    assert "0x3B808081u" in src and "0xAF7EFEFFu" in src and "0x4B000000u" in src
