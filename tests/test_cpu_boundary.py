@@ -126,11 +126,22 @@ def test_plan_records_of_the_engine():
     from acr_b200.engine import Engine
     eng = Engine(None, 2, "cpu", dry_run=True)
     kinds = [r["kind"] for r in eng.recs]
-    # 348 Conv2d of the reference: conv1 runs as im2col + 1x1 (+1), the two contact_layers[4|5] convs are folded 1x1
-    # launches (counted), the eight head stems run as two merged convs (-6)
-    assert kinds.count(L.OP_CONV) == 341 and kinds.count(L.OP_IM2COL_STEM) == 1 and kinds.count(L.OP_STEM) == 0
+    # 348 Conv2d of the reference: conv1 runs as its own fused tcgen05 kernel (csrc/stem_tc.cu), the two
+    # contact_layers[4|5] convs are folded 1x1 launches (counted), the eight head stems run as two merged convs (-6)
+    assert kinds.count(L.OP_CONV) == 340 and kinds.count(L.OP_STEM_TC) == 1 and kinds.count(L.OP_IM2COL_STEM) == 0
+    assert kinds.count(L.OP_STEM) == 0 and kinds[0] == L.OP_STEM_TC
     assert kinds.count(L.OP_FUSE) == 23 and kinds.count(L.OP_POOL) == 1 and kinds.count(L.OP_PARTHEAD) == 1
-    assert eng.n_ops == len(kinds) == 369
+    assert eng.n_ops == len(kinds) == 368
+    # ACR_B200_STEM_FUSED=0: round 1's im2col (27 normalised taps -> 32 channels) + a 1x1 tcgen05 conv
+    os.environ["ACR_B200_STEM_FUSED"] = "0"
+    try:
+        k0 = [r["kind"] for r in Engine(None, 2, "cpu", dry_run=True).recs]
+    finally:
+        del os.environ["ACR_B200_STEM_FUSED"]
+    assert k0.count(L.OP_CONV) == 341 and k0.count(L.OP_IM2COL_STEM) == 1 and len(k0) == 369
+    # frame sizes whose tile counts are not powers of two keep the im2col stem (stem_tc.cu indexes tiles with shifts)
+    k384 = [r["kind"] for r in Engine(None, 1, "cpu", dry_run=True, input_size=384).recs]
+    assert k384.count(L.OP_STEM_TC) == 0 and k384.count(L.OP_IM2COL_STEM) == 1
     # opt-in (ACR_B200_FOLD_FUSE=1): the 15 fuse sums of the coarser outputs run inside the stride-2 conv of their finer neighbour
     from acr_b200.netspec import build_acr_spec
     spec = build_acr_spec(512, fold_fuse=True)

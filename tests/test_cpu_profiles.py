@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-R1_PLAN = {"ACR_B200_MERGE_STEMS": "0", "ACR_B200_FOLD_FUSE": "0"}   # the round-1 captures are of the round-1 plan
+R1_PLAN = {"ACR_B200_MERGE_STEMS": "0", "ACR_B200_FOLD_FUSE": "0", "ACR_B200_STEM_FUSED": "0"}   # the round-1 captures are of the round-1 plan
 
 
 def _run(*args, env=None):

@@ -32,9 +32,9 @@ def test_fp32_and_heads_only_plan_layouts():
     full16 = Engine(None, 2, "cpu", torch.bfloat16, dry_run=True)
     full32 = Engine(None, 2, "cpu", torch.float32, dry_run=True)
     heads = Engine(None, 2, "cpu", torch.bfloat16, dry_run=True, head_only=True)
-    # fp32 plan: CUDA-core stem instead of im2col + 1x1 (one launch less), every conv on the validation kernel
-    assert full32.n_ops == full16.n_ops - 1
-    assert all(r["kind"] != L.OP_CONV and r["kind"] != L.OP_IM2COL_STEM for r in full32.recs)
+    # fp32 plan: CUDA-core stem where the 16-bit plan has the fused tcgen05 stem, every conv on the validation kernel
+    assert full32.n_ops == full16.n_ops
+    assert all(r["kind"] not in (L.OP_CONV, L.OP_IM2COL_STEM, L.OP_STEM_TC) for r in full32.recs)
     assert 1.9 < full32.arena_bytes / full16.arena_bytes < 2.1
     # heads-only plan = the ops from the coord concat on; the external feature buffer is allocated up front
     first = next(i for i, r in enumerate(full16.recs) if r["kind"] == L.OP_COORD)

@@ -63,21 +63,46 @@ def _cmp(out, ref, tol):
     return worst
 
 
-@pytest.mark.parametrize("tc_stem", [True, False])
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
-def test_stem_vs_oracle(sd, image, tc_stem, dtype, tol):
-    """conv1 + bn1 + ReLU on uint8 frames (acr/model.py:831-835): the im2col + tcgen05 1x1 form and the
-    direct CUDA-core form against the oracle's fp32 conv (error = 16-bit rounding of taps/weights/output)."""
+def _stem_out(sd, image, dtype, form):
+    from acr_b200 import lib as L
     from acr_b200.engine import Engine
-    from oracle import net_ref
-    eng = Engine(sd, image.shape[0], "cuda", dtype, keep_extra=("t1_stem1",), stem_on_tensor_cores=tc_stem)
+    os.environ["ACR_B200_STEM_FUSED"] = "0" if form == "im2col" else "1"
+    try:
+        eng = Engine(sd, image.shape[0], "cuda", dtype, keep_extra=("t1_stem1",), stem_on_tensor_cores=form != "cuda_cores")
+    finally:
+        del os.environ["ACR_B200_STEM_FUSED"]
+    kinds = [r["kind"] for r in eng.recs]
+    want = {"fused": L.OP_STEM_TC, "im2col": L.OP_IM2COL_STEM, "cuda_cores": L.OP_STEM}[form]
+    assert kinds.count(want) == 1 and sum(kinds.count(k) for k in (L.OP_STEM_TC, L.OP_IM2COL_STEM, L.OP_STEM)) == 1
     eng.run(image.cuda())
     torch.cuda.synchronize()
-    got = eng.view("t1_stem1")[..., :64].permute(0, 3, 1, 2).float().cpu()
+    return eng.view("t1_stem1")[..., :64].permute(0, 3, 1, 2).float().cpu()
+
+
+@pytest.mark.parametrize("form", ["fused", "im2col", "cuda_cores"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
+def test_stem_vs_oracle(sd, image, form, dtype, tol):
+    """conv1 + bn1 + ReLU on uint8 frames (acr/model.py:831-835) in its three forms -- one tcgen05 kernel that builds the
+    im2col operand in shared memory (csrc/stem_tc.cu, the default), im2col + a 1x1 tcgen05 conv (ACR_B200_STEM_FUSED=0),
+    the direct CUDA-core kernel -- against the oracle's fp32 conv (error = 16-bit rounding of taps/weights/output)."""
+    from oracle import net_ref
+    got = _stem_out(sd, image, dtype, form)
     net = net_ref._Net(sd)
     x = (image.float().permute(0, 3, 1, 2) / 255.0) * 2.0 - 1.0
     ref = net.cbr(x, "backbone.conv1", "backbone.bn1", stride=2)
     assert rel_err(got.numpy(), ref.numpy()) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fused_stem_equals_the_im2col_form(sd, image, dtype):
+    """Same 16-bit taps, same 16-bit folded weights, fp32 accumulation in both: the two tensor-core forms may differ only
+    by the bias (added in fp32 by the conv epilogue, carried as a hi + lo 16-bit pair through the K dimension by the fused
+    kernel: 2^-17 relative) and by the summation order -- at most one 16-bit ulp of the output, on a handful of pixels."""
+    a, b = _stem_out(sd, image, dtype, "fused"), _stem_out(sd, image, dtype, "im2col")
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    diff = (a - b).abs()
+    assert (diff <= ulp * torch.maximum(a.abs(), b.abs()) + 1e-6).all(), float(diff.max())
+    assert (diff > 0).float().mean() < 0.02
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 1e-3), (torch.bfloat16, 4e-3)])

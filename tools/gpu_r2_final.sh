@@ -10,6 +10,8 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>> $OUT/z_ben
 FULL=1 bash tools/ncu_conv.sh r2_final > $OUT/z_ncu.log 2>&1
 python tools/layer_table.py kernels $OUT/launches_r2_final.csv > $OUT/z_kernels.md
 python tools/layer_table.py convs $OUT/conv_traffic_r2_final.csv > $OUT/z_convs.md
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stem_tc -s 3 -c 1 -f -o $OUT/r2_stem_full \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/z_ncu_stem.log 2>&1
 timeout 300 python tools/latency_bench.py > $OUT/z_latency.jsonl 2>&1
 tail -3 $OUT/z_pytest.log; python -c "
 import json
