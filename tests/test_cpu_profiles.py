@@ -49,20 +49,21 @@ def test_committed_bench_lines_carry_the_contract_keys():
 
 
 def test_round2_conv_traffic_and_tables_match_the_current_plan(tmp_path):
-    """The round-2 captures are of the current plan (341 conv launches: merged head stems)."""
+    """The round-2 captures are of the current plan (340 conv launches: merged head stems, conv1 in its own fused kernel)."""
     dst = str(tmp_path / "t.json")
     _run("tools/conv_traffic.py", "profiles/r2_final_conv_launches.csv", dst, env={"CONV_BUILD_ID": "x"})     # the current plan
     got, ref = json.load(open(dst)), json.load(open(os.path.join(ROOT, "profiles", "r2_conv_traffic.json")))
     for k in ("traffic_bytes", "algorithmic_bytes", "launches", "dram_read_bytes", "dram_write_bytes", "batch"):
         assert got[k] == ref[k], k
-    assert ref["launches"] == 341 and len(ref["conv_build_id"]) == 12
+    assert ref["launches"] == 340 and len(ref["conv_build_id"]) == 12
     assert 0.8 < ref["traffic_bytes"] / ref["algorithmic_bytes"] < 1.1
     convs = _run("tools/layer_table.py", "convs", "profiles/r2_final_conv_launches.csv")
-    assert "over 341 launches" in convs
+    assert "over 340 launches" in convs
     kernels = _run("tools/layer_table.py", "kernels", "profiles/r2_final_launches.csv")
     for k in ("conv_tc_kernel<64, __nv_bfloat16, 23>", "conv_tc_kernel<64, __nv_bfloat16, 19>", "conv_tc_kernel<64, __nv_bfloat16, 34>",
-              "pool_kernel", "mano_forward_kernel", "fuse_kernel"):
+              "stem_tc_kernel<__nv_bfloat16>", "pool_kernel", "mano_forward_kernel", "fuse_kernel"):
         assert k in kernels, k
+    assert "im2col" not in kernels
 
 
 def test_round2_bench_lines_carry_the_contract_keys():

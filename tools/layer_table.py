@@ -31,7 +31,8 @@ if mode == "kernels":
     tot = sum(r["gpu__time_duration.sum"] for r in rows)
     agg = collections.OrderedDict()
     for r in rows:
-        a = agg.setdefault(r["name"].split("(")[0], [0, 0.0])
+        name = r["name"].replace("acr::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("(anonymous namespace)::", "")
+        a = agg.setdefault(name.split("(")[0], [0, 0.0])
         a[0] += 1
         a[1] += r["gpu__time_duration.sum"]
     print("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
