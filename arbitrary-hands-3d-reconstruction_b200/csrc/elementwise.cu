@@ -511,6 +511,9 @@ __global__ void __launch_bounds__(256, 2) pool_kernel(TensorRef feat, TensorRef 
 
 int launch_pool(const TensorRef& feat, const TensorRef& logits, float* part, int batch, int act_dtype,
                 cudaStream_t st) {
+  if (pool_tc_enabled() && (act_dtype == ACR_DT_BF16 || act_dtype == ACR_DT_F16) && logits.H == 2 * feat.H && logits.W == 2 * feat.W &&
+      logits.C >= 33 && pool_tc_takes(feat, logits))
+    return launch_pool_tc(feat, logits, part, batch, act_dtype, st);     // tcgen05 / TMA form (pool_tc.cu)
   const int per = feat.H * feat.W / POOL_CHUNKS;
   ACR_CHECK_ARG(feat.C == 256 && logits.H == 2 * feat.H && logits.W == 2 * feat.W && logits.C >= 33 &&
                     (feat.H * feat.W) % POOL_CHUNKS == 0 && per % POOL_HALF == 0 &&

@@ -45,6 +45,10 @@ constexpr int POOL_CHUNKS = 16;
 constexpr int POOL_PART_FLOATS = 256 * 32 + 64;
 int launch_pool(const TensorRef& feat, const TensorRef& logits, float* part, int batch, int act_dtype,
                 cudaStream_t st);
+// pool_tc.cu: the same contraction on tcgen05 / TMEM fed by TMA; launch_pool uses it for the shapes it takes
+bool pool_tc_enabled();
+bool pool_tc_takes(const TensorRef& feat, const TensorRef& logits);
+int launch_pool_tc(const TensorRef& feat, const TensorRef& logits, float* part, int batch, int act_dtype, cudaStream_t st);
 struct PartHeadArgs {
   const float* part;           // pool partials
   float* pooled;               // (B,256,32) fp32 normalised attention-pooled features (output)

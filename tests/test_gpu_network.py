@@ -124,6 +124,26 @@ def test_attention_pooling_vs_torch(sd, image, dtype, tol):
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_pool_on_tcgen05_equals_the_mma_sync_form(sd, image, dtype):
+    """csrc/pool_tc.cu (tcgen05 / TMEM / TMA, one maximum per 1024-pixel chunk) against the warp-level mma.sync kernel it
+    replaces (ACR_B200_POOL_TC=0, running maximum per 512 pixels) on the same plan and frames: the two differ only in
+    which maximum the 16-bit weights were rounded against and in the summation order."""
+    from acr_b200.engine import Engine
+    eng = Engine(sd, image.shape[0], "cuda", dtype)
+    got = {}
+    for form in ("1", "0"):
+        os.environ["ACR_B200_POOL_TC"] = form
+        try:
+            eng.run(image.cuda())
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["ACR_B200_POOL_TC"]
+        got[form] = eng.view("pooled").view(image.shape[0], 256, 32).clone()
+        assert torch.isfinite(got[form]).all()
+    assert rel_err(got["1"].cpu().numpy(), got["0"].cpu().numpy()) < (2e-3 if dtype == torch.bfloat16 else 3e-4)
+
+
 def test_plan_fp16_refconv_vs_oracle(sd, image, oracle_out):
     """Everything except the tensor-core conv (stem, fuse, bilinear, pooling, part head, plan wiring)."""
     _, out = _engine_maps(sd, image, ref_conv=True, dtype=torch.float16)
