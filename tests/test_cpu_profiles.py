@@ -61,7 +61,7 @@ def test_round2_conv_traffic_and_tables_match_the_current_plan(tmp_path):
     assert "over 340 launches" in convs
     kernels = _run("tools/layer_table.py", "kernels", "profiles/r2_final_launches.csv")
     for k in ("conv_tc_kernel<64, __nv_bfloat16, 23>", "conv_tc_kernel<64, __nv_bfloat16, 19>", "conv_tc_kernel<64, __nv_bfloat16, 34>",
-              "stem_tc_kernel<__nv_bfloat16>", "pool_kernel", "mano_forward_kernel", "fuse_kernel"):
+              "stem_tc_kernel<__nv_bfloat16>", "pool_tc_kernel<__nv_bfloat16>", "mano_forward_kernel", "fuse_kernel"):
         assert k in kernels, k
     assert "im2col" not in kernels
 
