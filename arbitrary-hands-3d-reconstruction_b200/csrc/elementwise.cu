@@ -551,20 +551,39 @@ __global__ void __launch_bounds__(256) parthead_kernel(PartHeadArgs a) {
     for (int c = 0; c < POOL_CHUNKS; ++c) s_scale[c][t] /= S;
   }
   __syncthreads();
-  for (int j = 0; j < 32; ++j) {
-    float v = 0.f;
-    for (int c = 0; c < POOL_CHUNKS; ++c) v = fmaf(part[(size_t)c * POOL_PART_FLOATS + t * 32 + j], s_scale[c][j], v);
-    s_pool[t][j] = v;
-    a.pooled[((size_t)b * 256 + t) * 32 + j] = v;
+  {  // merge the chunks: element e = channel * 32 + part of the [256][32] partial sums; thread t takes e = t + 256 i, so a warp
+     // reads 128 contiguous bytes per load and its part index (t & 31) never changes (same chunk order as before: same bits)
+    const int j = t & 31;
+    float sc[POOL_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < POOL_CHUNKS; ++c) sc[c] = s_scale[c][j];
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const int e = t + 256 * i;
+      float v = 0.f;
+#pragma unroll
+      for (int c = 0; c < POOL_CHUNKS; ++c) v = fmaf(__ldg(part + (size_t)c * POOL_PART_FLOATS + e), sc[c], v);
+      s_pool[e >> 5][j] = v;
+      a.pooled[(size_t)b * 256 * 32 + e] = v;
+    }
   }
   __syncthreads();
   // shape features: sf[c64][j] = W(64,256) . pooled[:, j] + b
-  for (int o = t; o < 64 * 32; o += 256) {
-    const int c64 = o >> 5, j = o & 31;
-    float v = a.shape_b[c64];
-    const float* w = a.shape_w + (size_t)c64 * 256;
-    for (int c = 0; c < 256; ++c) v = fmaf(w[c], s_pool[c][j], v);
-    s_sf[c64][j] = v;
+  {  // thread t: part j = t & 31, output channels c0 + 8 i -- one shared-memory read of pooled[c][j] serves eight outputs; every
+     // output still accumulates over c in ascending order (same bits as one output at a time)
+    const int j = t & 31, c0 = t >> 5;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = a.shape_b[c0 + 8 * i];
+    const float* w = a.shape_w + (size_t)c0 * 256;
+#pragma unroll 4
+    for (int c = 0; c < 256; ++c) {
+      const float x = s_pool[c][j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(__ldg(w + (size_t)i * 8 * 256 + c), x, v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_sf[c0 + 8 * i][j] = v[i];
   }
   // contact offsets: thread (side, joint, o)
   if (t < 192) {
