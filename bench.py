@@ -436,7 +436,9 @@ def run_b200(args):
         mano_gbs = lambda n, us: n * MANO_BYTES / us / 1e3
         conv_gflop = sum(2.0 * o.out.H * o.out.W * o.out.C * o.ins[0].C * o.attrs["k"] ** 2
                          for o in eng.spec.ops if o.kind == "conv") / 1e9
-        if eng.stem_on_tensor_cores:   # conv1 (3x3 s2, 3 -> 64) runs as im2col + a 1x1 tcgen05 conv: 27 real taps
+        if any(r["kind"] == L.OP_IM2COL_STEM for r in eng.recs):   # ACR_B200_STEM_FUSED=0: conv1 (3x3 s2, 3 -> 64) as im2col + a
+            # 1x1 conv_tc launch (27 real taps) is part of the conv launch set; the fused stem_tc_kernel (default) is timed and
+            # counted apart (profile_ms_by_kind["11"]), so neither its time nor its flops enter this roofline
             conv_gflop += sum(2.0 * o.out.H * o.out.W * 64 * 27 for o in eng.spec.ops if o.kind == "stem") / 1e9
         ach = conv_gflop * B / conv_ms if conv_ms else 0.0          # TFLOP/s (GFLOP/ms)
         img_s = world * B * args.steps / (ms_value / 1e3)
