@@ -82,6 +82,12 @@ def test_round2_bench_lines_carry_the_contract_keys():
         if n > 1:
             assert d["gather_check"] is True and len(d["ms_per_step_by_rank"]) == n
     d = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench_default.json")).read())
+    # the roofline's flops are those of the 340 conv_tc launches only: conv1 runs in stem_tc_kernel (timed as kind 11), so
+    # its 2 * 256 * 256 * 64 * 27 flops per image must not be credited to the conv kernels' time
+    stem_gflop = 2.0 * 256 * 256 * 64 * 27 / 1e9 * 256
+    assert abs(d["roofline"]["algorithmic_gflop_per_launch_set"] - (25819.4979 - stem_gflop)) < 0.5
+    assert "340 launches" in d["roofline"]["kernel"] and "11" in d["profile_ms_by_kind"]
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     assert d["cpu_baseline"]["kind"] == "reference" and {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     r = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench_reference.json")).read())
     assert r["impl"] == "reference" and r["cpu_baseline"]["kind"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
