@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 R1_PLAN = {"ACR_B200_MERGE_STEMS": "0", "ACR_B200_FOLD_FUSE": "0", "ACR_B200_STEM_FUSED": "0"}   # the round-1 captures are of the round-1 plan
 
@@ -91,3 +93,26 @@ def test_round2_bench_lines_carry_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "reference" and {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     r = json.loads(open(os.path.join(ROOT, "profiles", "r2_final_bench_reference.json")).read())
     assert r["impl"] == "reference" and r["cpu_baseline"]["kind"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_product_kernels_are_tcgen05_in_sass():
+    """cuobjdump of the in-tree library (cross-compiled here by build()): every instance of the conv, stem and pooling GEMM
+    kernels issues tcgen05.mma (UTCHMMA) with TMEM loads and mbarriers, the operand / result movers are TMA, and warp-level
+    HMMA exists only in the mma.sync pooling kernel kept as an opt-out."""
+    lib = os.path.join(ROOT, "arbitrary-hands-3d-reconstruction_b200", "lib", "libacr_b200.so")
+    if not (os.path.exists(lib) and os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("library not built or no cuobjdump")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import sass_audit
+        rows = sass_audit.audit(lib)
+    finally:
+        sys.path.pop(0)
+    gemm = {n: r for n, r in rows.items() if n.startswith(("conv_tc_kernel<", "stem_tc_kernel<", "pool_tc_kernel<"))}
+    assert len(gemm) >= 40
+    for n, r in gemm.items():
+        assert r["UTCHMMA"] > 0 and r["LDTM"] > 0 and r["UTCBAR"] > 0 and r["SYNCS"] > 0 and r["HMMA"] == 0, n
+        assert r["UTMALDG"] > 0 or n.startswith("stem_tc_kernel<"), n          # the stem builds its operand from uint8 itself
+        assert r["UTMASTG"] > 0 or n.startswith("pool_tc_kernel<"), n          # the pooling result is 32 KB of fp32 per CTA
+    assert {n for n, r in rows.items() if r["HMMA"]} == {"pool_kernel<__half>", "pool_kernel<__nv_bfloat16>"}
+    assert any(r["FFMA2"] for n, r in rows.items() if n.startswith("mano_forward_kernel"))
